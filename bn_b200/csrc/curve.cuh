@@ -1,0 +1,233 @@
+// curve.cuh -- Jacobian G1/G2 arithmetic and the optimal-ate line schedule, thread-per-element.
+//
+// Group law: the formulas and the control flow of reference src/groups/mod.rs:228-312 are kept exactly
+// (same doubling / addition formulas, same early returns, same MSB-first chain that skips leading zeros),
+// because the crate's G1/G2 values are un-normalised Jacobian triples: only the same chain of canonical
+// field operations reproduces the same (x, y, z) limbs.  The field arithmetic underneath is ours (fp.cuh).
+//
+// Line schedule: the 102 line evaluations of the ate loop (64 doublings + 36 additions + 2 Frobenius
+// additions; reference src/groups/mod.rs:557-634) are produced by ONE thread per pairing and streamed to
+// HBM in the order the Miller kernel consumes them, already multiplied by P's coordinates and by xi where
+// a lane of the Miller kernel needs the wrapped coefficient.  (The reference keeps them in a heap Vec.)
+#pragma once
+#include "fp2.cuh"
+
+namespace bn {
+
+struct FqOps {
+    typedef Fp T;
+    static BN_HD T add(const T& a, const T& b) { return fp_add<MQ>(a, b); }
+    static BN_HD T sub(const T& a, const T& b) { return fp_sub<MQ>(a, b); }
+    static BN_HD T neg(const T& a) { return fp_neg<MQ>(a); }
+    static BN_HD T mul(const T& a, const T& b) { return fp_mul<MQ>(a, b); }
+    static BN_HD T sqr(const T& a) { return fp_mul<MQ>(a, a); }
+    static BN_HD bool is_zero(const T& a) { return fp_is_zero(a); }
+    static BN_HD bool eq(const T& a, const T& b) { return fp_eq(a, b); }
+    static BN_HD T zero() { return fp_zero(); }
+    static BN_HD T one() { return fq_one(); }
+};
+struct Fq2Ops {
+    typedef Fp2 T;
+    static BN_HD T add(const T& a, const T& b) { return fp2_add(a, b); }
+    static BN_HD T sub(const T& a, const T& b) { return fp2_sub(a, b); }
+    static BN_HD T neg(const T& a) { return fp2_neg(a); }
+    static BN_HD T mul(const T& a, const T& b) { return fp2_mul(a, b); }
+    static BN_HD T sqr(const T& a) { return fp2_sqr(a); }
+    static BN_HD bool is_zero(const T& a) { return fp2_is_zero(a); }
+    static BN_HD bool eq(const T& a, const T& b) { return fp2_eq(a, b); }
+    static BN_HD T zero() { return fp2_zero(); }
+    static BN_HD T one() { return fp2_one(); }
+};
+
+template <class F>
+struct Jac {
+    typename F::T x, y, z;
+};
+
+// reference src/groups/mod.rs:228-247
+template <class F>
+BN_HD_NOINLINE Jac<F> jac_double(const Jac<F>& p) {
+    typedef typename F::T T;
+    T a = F::sqr(p.x);
+    T b = F::sqr(p.y);
+    T c = F::sqr(b);
+    T d = F::sub(F::sub(F::sqr(F::add(p.x, b)), a), c);
+    d = F::add(d, d);
+    T e = F::add(F::add(a, a), a);
+    T f = F::sqr(e);
+    T x3 = F::sub(f, F::add(d, d));
+    T eight_c = F::add(c, c);
+    eight_c = F::add(eight_c, eight_c);
+    eight_c = F::add(eight_c, eight_c);
+    T y1z1 = F::mul(p.y, p.z);
+    Jac<F> r;
+    r.x = x3;
+    r.y = F::sub(F::mul(e, F::sub(d, x3)), eight_c);
+    r.z = F::add(y1z1, y1z1);
+    return r;
+}
+
+// reference src/groups/mod.rs:272-312
+template <class F>
+BN_HD_NOINLINE Jac<F> jac_add(const Jac<F>& p, const Jac<F>& o) {
+    typedef typename F::T T;
+    if (F::is_zero(p.z)) return o;
+    if (F::is_zero(o.z)) return p;
+    T z1_squared = F::sqr(p.z);
+    T z2_squared = F::sqr(o.z);
+    T u1 = F::mul(p.x, z2_squared);
+    T u2 = F::mul(o.x, z1_squared);
+    T z1_cubed = F::mul(p.z, z1_squared);
+    T z2_cubed = F::mul(o.z, z2_squared);
+    T s1 = F::mul(p.y, z2_cubed);
+    T s2 = F::mul(o.y, z1_cubed);
+    if (F::eq(u1, u2) && F::eq(s1, s2)) return jac_double<F>(p);
+    T h = F::sub(u2, u1);
+    T s2_minus_s1 = F::sub(s2, s1);
+    T i = F::sqr(F::add(h, h));
+    T j = F::mul(h, i);
+    T r = F::add(s2_minus_s1, s2_minus_s1);
+    T v = F::mul(u1, i);
+    T s1_j = F::mul(s1, j);
+    T x3 = F::sub(F::sub(F::sqr(r), j), F::add(v, v));
+    Jac<F> out;
+    out.x = x3;
+    out.y = F::sub(F::mul(r, F::sub(v, x3)), F::add(s1_j, s1_j));
+    out.z = F::mul(F::sub(F::sub(F::sqr(F::add(p.z, o.z)), z1_squared), z2_squared), h);
+    return out;
+}
+
+// `G * Fr`: reference src/groups/mod.rs:250-270.  fr is the Montgomery image of the scalar (as stored in bn::Fr).
+template <class F>
+BN_HD Jac<F> jac_mul(const Jac<F>& p, const Fp& fr) {
+    Fp k = fp_from_mont<ModR>(fr);  // U256::from(Fr), reference src/fields/fp.rs:15-22
+    Jac<F> res;
+    res.x = F::zero();
+    res.y = F::one();
+    res.z = F::zero();  // G::zero(), reference src/groups/mod.rs:208-214
+    bool found_one = false;
+    for (int i = 255; i >= 0; i--) {
+        if (found_one) res = jac_double<F>(res);
+        uint32_t w = 0;
+        BN_UNROLL
+        for (int l = 0; l < 8; l++) w = ((i >> 5) == l) ? k.v[l] : w;
+        if ((w >> (i & 31)) & 1u) {
+            found_one = true;
+            res = jac_add<F>(res, p);
+        }
+    }
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Optimal-ate line schedule
+// ------------------------------------------------------------------------------------------------
+struct G2Proj {
+    Fp2 x, y, z;
+};
+// One line of the Miller loop as the hexad kernel consumes it.  As an Fq12 element (w^6 = xi):
+//   l0 + l3 w^3 + l4 w^4,   l0 = ell_0, l3 = ell_vw * P.y, l4 = ell_vv * P.x
+// (reference mul_by_024 slots, src/fields/fq12.rs:107-120, and the scaling at src/groups/mod.rs:502),
+// plus xi*l3 and xi*l4 for the lanes whose product index wraps past w^5.
+struct Line {
+    Fp2 l0, l3, xl3, l4, xl4;
+};
+#define BN_LINE_WORDS 80
+#define BN_NUM_LINES 102
+
+BN_HD Line make_line(const Fp2& ell_0, const Fp2& ell_vw, const Fp2& ell_vv, const Fp& px, const Fp& py) {
+    Line L;
+    L.l0 = ell_0;
+    L.l3 = fp2_mul_fp(ell_vw, py);
+    L.l4 = fp2_mul_fp(ell_vv, px);
+    L.xl3 = fp2_mul_xi(L.l3);
+    L.xl4 = fp2_mul_xi(L.l4);
+    return L;
+}
+
+// reference src/groups/mod.rs:612-634
+BN_HD_NOINLINE Line line_double(G2Proj& r, const Fp& px, const Fp& py) {
+    Fp2 a = fp2_half(fp2_mul(r.x, r.y));
+    Fp2 b = fp2_sqr(r.y);
+    Fp2 c = fp2_sqr(r.z);
+    Fp2 d = fp2_add(fp2_add(c, c), c);
+    Fp2 e = fp2_mul(g2_coeff_b(), d);
+    Fp2 f = fp2_add(fp2_add(e, e), e);
+    Fp2 g = fp2_half(fp2_add(b, f));
+    Fp2 h = fp2_sub(fp2_sqr(fp2_add(r.y, r.z)), fp2_add(b, c));
+    Fp2 i = fp2_sub(e, b);
+    Fp2 j = fp2_sqr(r.x);
+    Fp2 e_sq = fp2_sqr(e);
+    r.x = fp2_mul(a, fp2_sub(b, f));
+    r.y = fp2_sub(fp2_sqr(g), fp2_add(fp2_add(e_sq, e_sq), e_sq));
+    r.z = fp2_mul(b, h);
+    return make_line(fp2_mul_xi(i), fp2_neg(h), fp2_add(fp2_add(j, j), j), px, py);
+}
+
+// reference src/groups/mod.rs:592-610
+BN_HD_NOINLINE Line line_add(G2Proj& r, const Fp2& bx, const Fp2& by, const Fp& px, const Fp& py) {
+    Fp2 d = fp2_sub(r.x, fp2_mul(r.z, bx));
+    Fp2 e = fp2_sub(r.y, fp2_mul(r.z, by));
+    Fp2 f = fp2_sqr(d);
+    Fp2 g = fp2_sqr(e);
+    Fp2 h = fp2_mul(d, f);
+    Fp2 i = fp2_mul(r.x, f);
+    Fp2 j = fp2_sub(fp2_add(fp2_mul(r.z, g), h), fp2_add(i, i));
+    r.x = fp2_mul(d, j);
+    r.y = fp2_sub(fp2_mul(e, fp2_sub(i, j)), fp2_mul(h, r.y));
+    r.z = fp2_mul(r.z, h);
+    Fp2 ell_0 = fp2_mul_xi(fp2_sub(fp2_mul(e, bx), fp2_mul(d, by)));
+    return make_line(ell_0, d, fp2_neg(e), px, py);
+}
+
+// twisted Frobenius: reference src/groups/mod.rs:550-555
+BN_HD void g2_mul_by_q(Fp2& x, Fp2& y) {
+    x = fp2_mul(FROB_GAMMA_C[0][2], fp2_conj(x));
+    y = fp2_mul(FROB_GAMMA_C[0][3], fp2_conj(y));
+}
+
+// Affine coordinates of a (G1, G2) pair with ONE field inversion for both points
+// (reference to_affine, src/groups/mod.rs:113-130, inverts P.z and Q.z separately; the values are the same).
+// Returns false when either point is the point at infinity (pairing = one, src/groups/mod.rs:765-766).
+BN_HD bool pair_to_affine(const Jac<FqOps>& P, const Jac<Fq2Ops>& Q, Fp& px, Fp& py, Fp2& qx, Fp2& qy) {
+    bool inf = fp_is_zero(P.z) || fp2_is_zero(Q.z);
+    Wide n = wide_zero();
+    wide_mac2(n, Q.z.c0, Q.z.c0, Q.z.c1, Q.z.c1);
+    Fp nq = mont_reduce<MQ, 2>(n);         // |Q.z|^2 in Fq
+    Fp t = fp_mul<MQ>(P.z, nq);
+    Fp tinv = fp_inv<MQ>(fp_select(inf, fq_one(), t));
+    Fp pzinv = fp_mul<MQ>(tinv, nq);
+    Fp nqinv = fp_mul<MQ>(tinv, P.z);
+    Fp2 qzinv = Fp2{fp_mul<MQ>(Q.z.c0, nqinv), fp_neg<MQ>(fp_mul<MQ>(Q.z.c1, nqinv))};
+    Fp pz2 = fp_mul<MQ>(pzinv, pzinv);
+    px = fp_mul<MQ>(P.x, pz2);
+    py = fp_mul<MQ>(P.y, fp_mul<MQ>(pz2, pzinv));
+    Fp2 qz2 = fp2_sqr(qzinv);
+    qx = fp2_mul(Q.x, qz2);
+    qy = fp2_mul(Q.y, fp2_mul(qz2, qzinv));
+    return !inf;
+}
+
+// Emit the 102 lines for affine (P, Q) in Miller-loop order.  sink(index, line).
+// reference precompute, src/groups/mod.rs:557-588
+template <class Sink>
+BN_HD void ate_lines(const Fp& px, const Fp& py, const Fp2& qx, const Fp2& qy, Sink& sink) {
+    G2Proj r;
+    r.x = qx;
+    r.y = qy;
+    r.z = fp2_one();
+    int n = 0;
+    for (int b = BN_ATE_NBITS - 1; b >= 0; b--) {
+        sink(n++, line_double(r, px, py));
+        if ((BN_ATE_BITS >> b) & 1ULL) sink(n++, line_add(r, qx, qy, px, py));
+    }
+    Fp2 q1x = qx, q1y = qy;
+    g2_mul_by_q(q1x, q1y);
+    Fp2 q2x = q1x, q2y = q1y;
+    g2_mul_by_q(q2x, q2y);
+    q2y = fp2_neg(q2y);
+    sink(n++, line_add(r, q1x, q1y, px, py));
+    sink(n++, line_add(r, q2x, q2y, px, py));
+}
+
+}  // namespace bn

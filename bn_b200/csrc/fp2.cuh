@@ -1,0 +1,144 @@
+// fp2.cuh -- thread-local Fq2 = Fq[i]/(i^2+1) arithmetic (one thread owns the whole element).
+//
+// Replaces reference src/fields/fq2.rs:63-188 on canonical Montgomery values.  Used by the
+// thread-per-element kernels (line precomputation, G1/G2 scalar multiplication) and for the small
+// serial pieces of the hexad kernel.  Products are accumulated as 512-bit integers and reduced once
+// per output coefficient (2 reductions per Fq2 mul/sqr instead of the reference's 3-4 Montgomery muls).
+#pragma once
+#include "fp.cuh"
+
+namespace bn {
+
+struct Fp2 {
+    Fp c0, c1;
+};
+
+#if defined(__CUDACC__)
+#define BN_CONST __constant__ const
+#else
+#define BN_CONST static const
+#endif
+#include "constants_tower.inc"
+
+typedef ModQ MQ;
+
+BN_HD Fp2 fp2_zero() { return Fp2{fp_zero(), fp_zero()}; }
+BN_HD Fp fq_one() {
+    Fp r;
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) r.v[i] = FQ_ONE_f(i);
+    return r;
+}
+BN_HD Fp2 fp2_one() { return Fp2{fq_one(), fp_zero()}; }
+BN_HD Fp2 g2_coeff_b() {  // 3/xi, reference src/groups/mod.rs:392-397
+    Fp2 r;
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) {
+        r.c0.v[i] = G2_B_f(i);
+        r.c1.v[i] = G2_B_f(8 + i);
+    }
+    return r;
+}
+BN_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+BN_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+BN_HD Fp2 fp2_select(bool c, const Fp2& a, const Fp2& b) {
+    return Fp2{fp_select(c, a.c0, b.c0), fp_select(c, a.c1, b.c1)};
+}
+BN_HD Fp2 fp2_add(const Fp2& a, const Fp2& b) { return Fp2{fp_add<MQ>(a.c0, b.c0), fp_add<MQ>(a.c1, b.c1)}; }
+BN_HD Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return Fp2{fp_sub<MQ>(a.c0, b.c0), fp_sub<MQ>(a.c1, b.c1)}; }
+BN_HD Fp2 fp2_neg(const Fp2& a) { return Fp2{fp_neg<MQ>(a.c0), fp_neg<MQ>(a.c1)}; }
+BN_HD Fp2 fp2_dbl(const Fp2& a) { return Fp2{fp_dbl<MQ>(a.c0), fp_dbl<MQ>(a.c1)}; }
+BN_HD Fp2 fp2_half(const Fp2& a) { return Fp2{fp_half<MQ>(a.c0), fp_half<MQ>(a.c1)}; }  // == scale(two_inv), groups/mod.rs:446-449
+BN_HD Fp2 fp2_conj(const Fp2& a) { return Fp2{a.c0, fp_neg<MQ>(a.c1)}; }                // frobenius_map(odd), fq2.rs:74-83
+
+// raw limb add without reduction (inputs canonical -> result < 2q < 2^255)
+BN_HD Fp fp_add_raw(const Fp& a, const Fp& b) {
+    Fp r;
+    (void)add8(r.v, a.v, b.v);
+    return r;
+}
+// 2q - a for a < 2q (lazy negation: result in (0, 2q], congruent to -a)
+BN_HD Fp fp_neg_2q(const Fp& a) {
+    Fp r;
+    uint32_t p2[8];
+    load_mod2<MQ>(p2);
+    (void)sub8(r.v, p2, a.v);
+    return r;
+}
+
+// (a0 + a1 i)(b0 + b1 i), schoolbook on 512-bit accumulators: 4 products, 2 reductions.
+// reference src/fields/fq2.rs:139-155 (Karatsuba + 3-4 reductions there; same canonical result).
+BN_HD Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+    Fp nb1 = fp_neg_lazy<MQ>(b.c1);
+    Wide t0 = wide_zero(), t1 = wide_zero();
+    wide_mac2(t0, a.c0, b.c0, a.c1, nb1);   // a0 b0 - a1 b1   (< 2 q^2)
+    wide_mac2(t1, a.c0, b.c1, a.c1, b.c0);  // a0 b1 + a1 b0
+    return Fp2{mont_reduce<MQ, 2>(t0), mont_reduce<MQ, 2>(t1)};
+}
+// (a0+a1)(a0-a1) + 2 a0 a1 i.   reference src/fields/fq2.rs:112-123
+BN_HD Fp2 fp2_sqr(const Fp2& a) {
+    Fp s = fp_add_raw(a.c0, a.c1);                      // < 2q
+    Fp d = fp_add_raw(a.c0, fp_neg_lazy<MQ>(a.c1));     // a0 + (q - a1) in (0, 2q)
+    Wide t0 = wide_zero(), t1 = wide_zero();
+    wide_mac1(t0, s, d);  // < 4 q^2 -> raw < 1.76 q
+    wide_mac1(t1, a.c0, a.c1);
+    wide_dbl(t1);
+    return Fp2{mont_reduce<MQ, 2>(t0), mont_reduce<MQ, 2>(t1)};
+}
+// scale by an Fq element.   reference src/fields/fq2.rs:63-68
+BN_HD Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return Fp2{fp_mul<MQ>(a.c0, k), fp_mul<MQ>(a.c1, k)}; }
+
+// v (9 limbs, < 16q) -> v mod q by binary conditional subtraction of 8q, 4q, 2q, q.
+BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out) {
+    BN_UNROLL
+    for (int sh = 3; sh >= 0; sh--) {
+        uint32_t kq[9], t[9];
+        BN_UNROLL
+        for (int i = 0; i < 9; i++) {
+            uint32_t lo = (i < 8) ? MQ::m(i) : 0u;
+            uint32_t prev = (i > 0) ? MQ::m(i - 1) : 0u;
+            kq[i] = (sh == 0) ? lo : ((lo << sh) | (prev >> (32 - sh)));
+        }
+        uint32_t bw = sub8(t, v, kq);
+        int32_t top = (int32_t)v[8] - (int32_t)kq[8] - (int32_t)bw;  // all three are tiny
+        bool neg = top < 0;
+        t[8] = (uint32_t)top;
+        BN_UNROLL
+        for (int i = 0; i < 9; i++) v[i] = neg ? v[i] : t[i];
+    }
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) out[i] = v[i];
+}
+
+// multiply by xi = 9 + i:  (9x - y) + (9y + x) i.   reference src/fields/fq2.rs:70-72 (a full Fq2 mul there)
+BN_HD Fp2 fp2_mul_xi(const Fp2& a) {
+    Fp2 r;
+    // component 0: 9*a0 + (q - a1)  in (0, 10q];  component 1: 9*a1 + a0 in [0, 10q)
+    BN_UNROLL
+    for (int comp = 0; comp < 2; comp++) {
+        const Fp& x = comp == 0 ? a.c0 : a.c1;
+        Fp addend = comp == 0 ? fp_neg_lazy<MQ>(a.c1) : a.c0;
+        uint32_t v[9];
+        // v = x << 3
+        v[0] = x.v[0] << 3;
+        BN_UNROLL
+        for (int i = 1; i < 8; i++) v[i] = (x.v[i] << 3) | (x.v[i - 1] >> 29);
+        v[8] = x.v[7] >> 29;
+        uint32_t c = addi8(v, x.v);
+        v[8] += c;
+        c = addi8(v, addend.v);
+        v[8] += c;
+        fp_small_reduce9(v, comp == 0 ? r.c0.v : r.c1.v);
+    }
+    return r;
+}
+
+// 1/a.   reference src/fields/fq2.rs:125-136.  a != 0.
+BN_HD Fp2 fp2_inv(const Fp2& a) {
+    Wide n = wide_zero();
+    wide_mac2(n, a.c0, a.c0, a.c1, a.c1);
+    Fp t = fp_inv<MQ>(mont_reduce<MQ, 2>(n));
+    return Fp2{fp_mul<MQ>(a.c0, t), fp_neg<MQ>(fp_mul<MQ>(a.c1, t))};
+}
+
+}  // namespace bn

@@ -1,0 +1,266 @@
+// hexad.cuh -- Fq12 / Gt arithmetic spread over SIX lanes of a warp ("hexad"), registers only.
+//
+// Representation.  The reference's tower Fq12 = Fq6[w]/(w^2 - v), Fq6 = Fq2[v]/(v^3 - xi)
+// (src/fields/fq12.rs:26-31, src/fields/fq6.rs:42-48) is the same ring as Fq2[w]/(w^6 - xi):
+//     c0.c0 + c1.c0 w + c0.c1 w^2 + c1.c1 w^3 + c0.c2 w^4 + c1.c2 w^5 .
+// Lane k of a hexad (k = lane % 6; five hexads per warp, lanes 30/31 idle) holds the Fq2 coefficient g_k
+// of w^k of EVERY live Fq12 value, so a whole Gt costs 16 registers per lane and the final exponentiation's
+// half-dozen live values stay in the register file: no shared-memory or local-memory round trips for state.
+//
+// Multiplication is the length-6 negacyclic-style convolution
+//     c_k = sum_{i+j=k} a_i b_j + xi * sum_{i+j=k+6} a_i b_j
+// evaluated one Fq2 product per lane per step; operands travel between lanes with warp shuffles, the sender
+// choosing between a_i and xi*a_i, and the products of a lane are summed as 512-bit integers and reduced once
+// (2 Montgomery reductions per lane per Fq12 operation).  Results are canonical, hence bit-identical to the
+// reference's Karatsuba tower (src/fields/fq12.rs:275-307, src/fields/fq6.rs:113-158) which computes the same
+// ring element.
+//
+// All functions are collective over the hexad: every lane calls them with its own coefficient.
+// `Ctx` supplies k() and shfl(value, source lane index within the hexad); kernels.cu binds it to
+// __shfl_sync, tests/host_emu binds it to a barrier exchange between six host threads.
+#pragma once
+#include "fp2.cuh"
+
+namespace bn {
+
+// acc0 + acc1 i += x * y.  LAZY=false: y canonical (y1 negated as q - y1, each product < q^2);
+// LAZY=true: components of x, y < 2q (y1 negated as 2q - y1, each product < 4 q^2).
+template <bool LAZY>
+BN_HD void mac_fp2(Wide& acc0, Wide& acc1, const Fp2& x, const Fp2& y) {
+    Fp ny1 = LAZY ? fp_neg_2q(y.c1) : fp_neg_lazy<MQ>(y.c1);
+    wide_mac2(acc0, x.c0, y.c0, x.c1, ny1);
+    wide_mac2(acc1, x.c0, y.c1, x.c1, y.c0);
+}
+BN_HD Fp2 reduce2(const Wide& acc0, const Wide& acc1) {
+    return Fp2{mont_reduce<MQ, 4>(acc0), mont_reduce<MQ, 4>(acc1)};
+}
+BN_HD int nib(uint32_t packed, int k) { return (int)((packed >> (4 * k)) & 7u); }
+BN_HD int mod6(int x) { return x >= 6 ? x - 6 : x; }
+
+// the multiplicative identity: lane 0 holds 1
+template <class Ctx>
+BN_HD Fp2 hx_one(const Ctx& c) {
+    return fp2_select(c.k() == 0, fp2_one(), fp2_zero());
+}
+
+// conjugation over Fq6 (w -> -w) == reference unitary_inverse, src/fields/fq12.rs:103-105
+template <class Ctx>
+BN_HD Fp2 hx_conj(const Ctx& c, const Fp2& a) {
+    return fp2_select((c.k() & 1) != 0, fp2_neg(a), a);
+}
+
+// dense product.  reference src/fields/fq12.rs:295-307
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_mul(const Ctx& c, const Fp2& a, const Fp2& b) {
+    const int k = c.k();
+    Fp2 xa = fp2_mul_xi(a);
+    Wide acc0 = wide_zero(), acc1 = wide_zero();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = 0; s < 6; s++) {
+        // receiver k takes a_j from j = k - s (mod 6); the pair (j, s) wraps past w^5 iff j + s >= 6
+        Fp2 send = fp2_select(k + s >= 6, xa, a);
+        Fp2 x = c.shfl(send, mod6(k + 6 - s));
+        Fp2 y = c.shfl(b, s);
+        mac_fp2<false>(acc0, acc1, x, y);  // 6 steps * 2 q^2 per accumulator -> < 12 q^2
+    }
+    return reduce2(acc0, acc1);
+}
+
+// square.  reference src/fields/fq12.rs:275-282.  21 distinct products in 4 lock-step rounds:
+//   rounds 1-2: cross terms (doubled afterwards on the 512-bit accumulators)
+//   round 3   : even lanes a_i^2, odd lanes their third cross term (sender pre-doubles)
+//   round 4   : even lanes xi * a_j^2, odd lanes idle
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_sqr(const Ctx& c, const Fp2& a) {
+    const int k = c.k();
+    Fp2 xa = fp2_mul_xi(a);
+    Fp2 d = fp2_dbl(fp2_select(k == 4, xa, a));  // lane 3 sends 2 a_3, lane 4 sends 2 xi a_4 in round 3
+    Wide acc0 = wide_zero(), acc1 = wide_zero();
+    {   // round 1: lane0: xi a5 * a1 ; lane k>0: a0 * a_k
+        Fp2 x = c.shfl(fp2_select(k == 5, xa, a), nib(0x000005u, k));
+        Fp2 y = c.shfl(a, nib(0x543211u, k));
+        mac_fp2<false>(acc0, acc1, x, y);
+    }
+    {   // round 2: xi a4 a2 | xi a5 a2 | xi a5 a3 | a1 a2 | a1 a3 | a1 a4
+        Fp2 x = c.shfl(fp2_select(k >= 4, xa, a), nib(0x111554u, k));
+        Fp2 y = c.shfl(a, nib(0x432322u, k));
+        mac_fp2<false>(acc0, acc1, x, y);
+    }
+    wide_dbl(acc0);
+    wide_dbl(acc1);
+    {   // round 3: a0 a0 | (2 xi a4) a3 | a1 a1 | (2 xi a4) a5 | a2 a2 | (2 a3) a2
+        Fp2 x = c.shfl(fp2_select(k == 3 || k == 4, d, a), nib(0x324140u, k));
+        Fp2 y = c.shfl(a, nib(0x225130u, k));
+        mac_fp2<false>(acc0, acc1, x, y);
+    }
+    {   // round 4: xi a3 a3 | - | xi a4 a4 | - | xi a5 a5 | -
+        Fp2 x = c.shfl(xa, nib(0x050403u, k));
+        Fp2 y = c.shfl(a, nib(0x050403u, k));
+        y = fp2_select((k & 1) != 0, fp2_zero(), y);
+        mac_fp2<false>(acc0, acc1, x, y);
+    }
+    return reduce2(acc0, acc1);  // < (2+2)*2 + 2 + 2 = 12 q^2
+}
+
+// product with the sparse line l0 + l3 w^3 + l4 w^4 (reference mul_by_024, src/fields/fq12.rs:107-176).
+// l3k / l4k are ALREADY the variant this lane needs:  l3k = (k < 3 ? xi*l3 : l3), l4k = (k < 4 ? xi*l4 : l4).
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx& c, const Fp2& a, const Fp2& l0, const Fp2& l3k, const Fp2& l4k) {
+    const int k = c.k();
+    Wide acc0 = wide_zero(), acc1 = wide_zero();
+    mac_fp2<false>(acc0, acc1, a, l0);
+    Fp2 x3 = c.shfl(a, mod6(k + 3));  // a_{k-3}
+    mac_fp2<false>(acc0, acc1, x3, l3k);
+    Fp2 x4 = c.shfl(a, mod6(k + 2));  // a_{k-4}
+    mac_fp2<false>(acc0, acc1, x4, l4k);
+    return reduce2(acc0, acc1);
+}
+
+// product with an Fq6 element m0 + m1 v + m2 v^2 = m0 + m1 w^2 + m2 w^4 known to every lane.
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx& c, const Fp2& a, const Fp2& m0, const Fp2& m1, const Fp2& m2) {
+    const int k = c.k();
+    Fp2 m1k = fp2_select(k < 2, fp2_mul_xi(m1), m1);
+    Fp2 m2k = fp2_select(k < 4, fp2_mul_xi(m2), m2);
+    Wide acc0 = wide_zero(), acc1 = wide_zero();
+    mac_fp2<false>(acc0, acc1, a, m0);
+    Fp2 x2 = c.shfl(a, mod6(k + 4));  // a_{k-2}
+    mac_fp2<false>(acc0, acc1, x2, m1k);
+    Fp2 x4 = c.shfl(a, mod6(k + 2));  // a_{k-4}
+    mac_fp2<false>(acc0, acc1, x4, m2k);
+    return reduce2(acc0, acc1);
+}
+
+// Frobenius x -> x^(q^p), p in {1,2,3}: conj^p on each coefficient, times xi^(k (q^p-1)/6).
+// reference src/fields/fq12.rs:90-95 with the tables at fq12.rs:7-24, fq6.rs:5-40.
+template <class Ctx>
+BN_HD Fp2 hx_frob(const Ctx& c, const Fp2& a, int p) {
+    Fp2 t = (p & 1) ? fp2_conj(a) : a;
+    return fp2_mul(t, FROB_GAMMA_C[p - 1][c.k()]);
+}
+
+// Granger-Scott squaring of an element of the cyclotomic subgroup (reference src/fields/fq12.rs:178-227).
+// Fq12 = Fq4[w]/(w^3 - s), Fq4 = Fq2[s]/(s^2 - xi), s = w^3: the three Fq4 coefficients are the lane pairs
+// (0,3), (1,4), (2,5).  Each pair is squared with one Fq2 product per lane
+//   (x + y s)^2 = [(x+y)(x + xi y) - xy - xi xy] + [2xy] s .
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx& c, const Fp2& a) {
+    const int k = c.k();
+    const bool pre = (k & 1) == 0;  // lanes 0,2,4 form (x+y)(x+xi y); lanes 3,5,1 form x*y
+    // pair assignment: lane0,3 <- (g0,g3); lane2,5 <- (g1,g4); lane4,1 <- (g2,g5)
+    const int lo = nib(0x120120u, k), hi = lo + 3;
+    Fp2 xa = fp2_mul_xi(a);
+    Fp2 x = c.shfl(a, lo);
+    Fp2 y = c.shfl(a, hi);
+    Fp2 xy = c.shfl(xa, hi);
+    Fp2 f0, f1;  // factors, components < 2q
+    f0.c0 = fp_add_raw(x.c0, fp_select(pre, y.c0, fp_zero()));
+    f0.c1 = fp_add_raw(x.c1, fp_select(pre, y.c1, fp_zero()));
+    f1.c0 = fp_add_raw(fp_select(pre, xy.c0, y.c0), fp_select(pre, x.c0, fp_zero()));
+    f1.c1 = fp_add_raw(fp_select(pre, xy.c1, y.c1), fp_select(pre, x.c1, fp_zero()));
+    Wide acc0 = wide_zero(), acc1 = wide_zero();
+    mac_fp2<true>(acc0, acc1, f0, f1);  // < 8 q^2
+    Fp2 r = reduce2(acc0, acc1);
+    // partner product: lane0 <- lane3, lane2 <- lane5, lane4 <- lane1
+    Fp2 tmp = c.shfl(r, nib(0x010503u, k));
+    Fp2 r2 = fp2_add(r, r);
+    // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*t5 on lane 1
+    Fp2 xo = fp2_mul_xi(fp2_select(pre, tmp, r2));
+    Fp2 t_pre = fp2_sub(fp2_sub(r, tmp), xo);               // t0 / t2 / t4
+    Fp2 t_im = fp2_select(k == 1, xo, r2);                   // t1 / t3 / xi*t5
+    Fp2 t = fp2_select(pre, t_pre, t_im);
+    // pre lanes: 3t - 2z = 2(t - z) + t ; other lanes: 3t + 2z = 2(t + z) + t   (statement order of fq12.rs:198-221)
+    Fp2 z = fp2_add(t, fp2_select(pre, fp2_neg(a), a));
+    return fp2_add(fp2_add(z, z), t);
+}
+
+// f^u then conjugate (reference exp_by_neg_z, src/fields/fq12.rs:97-101, 229-246): plain square-and-multiply
+// on the 63 bits of u, first multiply folded into the initial value.
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_exp_by_neg_z(const Ctx& c, const Fp2& a) {
+    Fp2 res = a;
+    for (int b = 61; b >= 0; b--) {
+        res = hx_cyc_sqr(c, res);
+        if ((BN_U_PARAM >> b) & 1ULL) res = hx_mul(c, a, res);
+    }
+    return hx_conj(c, res);
+}
+
+// 1/f for f != 0.  reference src/fields/fq12.rs:284-292 -> fq6.rs:129-141 -> fq2.rs:125-136.
+// f^-1 = conj(f) * N^-1 with N = f * conj(f) in Fq6; the small Fq6/Fq2/Fq inversion chain is done
+// redundantly by every lane (it is a handful of Fq2 products next to one Fq inversion).
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_inv(const Ctx& c, const Fp2& f) {
+    Fp2 fc = hx_conj(c, f);
+    Fp2 n = hx_mul(c, f, fc);  // odd coefficients are zero
+    Fp2 n0 = c.shfl(n, 0), n1 = c.shfl(n, 2), n2 = c.shfl(n, 4);
+    // Fq6 inverse, reference src/fields/fq6.rs:129-141
+    Fp2 t0 = fp2_sub(fp2_sqr(n0), fp2_mul(n1, fp2_mul_xi(n2)));
+    Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(n2)), fp2_mul(n0, n1));
+    Fp2 t2 = fp2_sub(fp2_sqr(n1), fp2_mul(n0, n2));
+    Fp2 dd = fp2_add(fp2_mul_xi(fp2_add(fp2_mul(n2, t1), fp2_mul(n1, t2))), fp2_mul(n0, t0));
+    Fp2 di = fp2_inv(dd);
+    return hx_mul_fq6(c, fc, fp2_mul(di, t0), fp2_mul(di, t1), fp2_mul(di, t2));
+}
+
+// reference final_exponentiation, src/fields/fq12.rs:41-88 (same operation chain, hence the same exponent
+// (q^6-1)(q^2+1) * 2u(6u^2+3u+1)(q^4-q^2+1)/r that the crate's Gt values carry).
+template <class Ctx>
+BN_HD Fp2 hx_final_exp(const Ctx& c, const Fp2& f) {
+    // first chunk
+    Fp2 s;
+    {
+        Fp2 b = hx_inv(c, f);
+        Fp2 a = hx_conj(c, f);
+        Fp2 cc = hx_mul(c, a, b);
+        Fp2 d = hx_frob(c, cc, 2);
+        s = hx_mul(c, d, cc);
+    }
+    // last chunk
+    Fp2 a = hx_exp_by_neg_z(c, s);
+    Fp2 b = hx_cyc_sqr(c, a);
+    Fp2 cq = hx_cyc_sqr(c, b);
+    Fp2 d = hx_mul(c, cq, b);
+    Fp2 e = hx_exp_by_neg_z(c, d);
+    Fp2 ff = hx_cyc_sqr(c, e);
+    Fp2 g = hx_exp_by_neg_z(c, ff);
+    Fp2 h = hx_conj(c, d);
+    Fp2 i = hx_conj(c, g);
+    Fp2 j = hx_mul(c, i, e);
+    Fp2 kk = hx_mul(c, j, h);
+    Fp2 l = hx_mul(c, kk, b);
+    Fp2 m = hx_mul(c, kk, e);
+    Fp2 n = hx_mul(c, s, m);
+    Fp2 o = hx_frob(c, l, 1);
+    Fp2 p = hx_mul(c, o, n);
+    Fp2 q = hx_frob(c, kk, 2);
+    Fp2 r = hx_mul(c, q, p);
+    Fp2 ss = hx_conj(c, s);
+    Fp2 t = hx_mul(c, ss, l);
+    Fp2 u = hx_frob(c, t, 3);
+    return hx_mul(c, u, r);
+}
+
+// Gt::pow, reference src/fields/mod.rs:35-46 via src/lib.rs:171: 256 squarings, generic (non-cyclotomic).
+// e = plain (de-Montgomerised) exponent, identical in all six lanes.
+template <class Ctx>
+BN_HD Fp2 hx_pow(const Ctx& c, const Fp2& a, const Fp& e) {
+    Fp2 res = hx_one(c);
+    for (int i = 255; i >= 0; i--) {
+        res = hx_sqr(c, res);
+        uint32_t w = 0;
+        BN_UNROLL
+        for (int l = 0; l < 8; l++) w = ((i >> 5) == l) ? e.v[l] : w;
+        bool bit = (w >> (i & 31)) & 1u;
+        Fp2 prod = hx_mul(c, a, res);  // computed by all hexads of the warp; selected per hexad
+        res = fp2_select(bit, prod, res);
+    }
+    return res;
+}
+
+// memory layout of bn::Gt (c[2][3][2][4] u64): coefficient g_k sits at Fq2 index (k&1)*3 + (k>>1)
+BN_HD int gt_slot(int k) { return (k & 1) * 3 + (k >> 1); }
+
+}  // namespace bn

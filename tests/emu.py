@@ -1,0 +1,88 @@
+"""ctypes driver for tests/host_emu/libemu.so (host emulation of the kernel arithmetic; test infra only)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu")
+_SO = os.path.join(_HERE, "libemu.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "emu.cpp")
+        csrc = os.path.join(os.path.dirname(_HERE), "..", "bn_b200", "csrc")
+        deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".inc"))]
+        if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", _SO, src, "-lpthread"])
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def fp_op(op, which, a, b=None):
+    a, b = _c(a), _c(b)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().emu_fp_op(op, which, _p(a), _p(b), _p(out))
+    return out
+
+
+def fp2_op(op, a, b=None):
+    a, b = _c(a), _c(b)
+    out = np.zeros(8, dtype=np.uint64)
+    lib().emu_fp2_op(op, _p(a), _p(b), _p(out))
+    return out
+
+
+def g1_mul(p, fr):
+    p, fr = _c(p), _c(fr)
+    out = np.zeros(12, dtype=np.uint64)
+    lib().emu_g1_mul(_p(p), _p(fr), _p(out))
+    return out
+
+
+def g2_mul(p, fr):
+    p, fr = _c(p), _c(fr)
+    out = np.zeros(24, dtype=np.uint64)
+    lib().emu_g2_mul(_p(p), _p(fr), _p(out))
+    return out
+
+
+def lines(g1, g2):
+    g1, g2 = _c(g1), _c(g2)
+    out = np.zeros((102, 40), dtype=np.uint64)
+    pa = np.zeros(8, dtype=np.uint64)
+    qa = np.zeros(16, dtype=np.uint64)
+    finite = lib().emu_lines(_p(g1), _p(g2), _p(out), _p(pa), _p(qa))
+    return finite, out, pa, qa
+
+
+def gt_op(op, a, b=None, arg=0):
+    a, b = _c(a), _c(b)
+    out = np.zeros(48, dtype=np.uint64)
+    lib().emu_gt_op(op, _p(a), _p(b), arg, _p(out))
+    return out
+
+
+def miller(lines_arr):
+    l = _c(lines_arr)
+    out = np.zeros(48, dtype=np.uint64)
+    lib().emu_miller(_p(l), _p(out))
+    return out
+
+
+def pairing(g1, g2):
+    g1, g2 = _c(g1), _c(g2)
+    out = np.zeros(48, dtype=np.uint64)
+    lib().emu_pairing(_p(g1), _p(g2), _p(out))
+    return out

@@ -1,0 +1,206 @@
+// Host emulation of the kernels' arithmetic (TEST INFRASTRUCTURE, never shipped, never a fallback).
+//
+// Compiles bn_b200/csrc/*.cuh with g++: the PTX carry chains are replaced by their portable C
+// equivalents (fp.cuh, #else branches) and a hexad's six lanes are six host threads that exchange
+// registers through a barrier instead of __shfl_sync.  tests/test_host_emu.py checks these entry points
+// against the oracle, so the tower / lane choreography / line schedule is validated without a GPU;
+// the -m gpu tests then validate the real kernels (PTX included) through the C ABI.
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../bn_b200/csrc/pairing.cuh"
+
+using namespace bn;
+
+namespace {
+
+struct Barrier {
+    std::atomic<int> count{0};
+    std::atomic<int> gen{0};
+    int n;
+    explicit Barrier(int n_) : n(n_) {}
+    void wait() {
+        int g = gen.load();
+        if (count.fetch_add(1) + 1 == n) {
+            count.store(0);
+            gen.fetch_add(1);
+        } else {
+            while (gen.load() == g) std::this_thread::yield();
+        }
+    }
+};
+
+struct HostHexShared {
+    Fp2 slot[6];
+    Barrier bar{6};
+};
+
+struct HostCtx {
+    int kk;
+    HostHexShared* sh;
+    int k() const { return kk; }
+    Fp2 shfl(const Fp2& v, int src) const {
+        sh->slot[kk] = v;
+        sh->bar.wait();
+        Fp2 r = sh->slot[src];
+        sh->bar.wait();
+        return r;
+    }
+};
+
+Fp load_fp(const uint64_t* p) {
+    Fp r;
+    for (int i = 0; i < 4; i++) {
+        r.v[2 * i] = (uint32_t)p[i];
+        r.v[2 * i + 1] = (uint32_t)(p[i] >> 32);
+    }
+    return r;
+}
+void store_fp(uint64_t* p, const Fp& a) {
+    for (int i = 0; i < 4; i++) p[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+}
+Fp2 load_fp2(const uint64_t* p) { return Fp2{load_fp(p), load_fp(p + 4)}; }
+void store_fp2(uint64_t* p, const Fp2& a) {
+    store_fp(p, a.c0);
+    store_fp(p + 4, a.c1);
+}
+
+// run fn(ctx) on six lanes
+template <class Fn>
+void run_hexad(Fn fn) {
+    HostHexShared sh;
+    std::vector<std::thread> th;
+    for (int k = 0; k < 6; k++) th.emplace_back([&sh, k, &fn]() { HostCtx c{k, &sh}; fn(c); });
+    for (auto& t : th) t.join();
+}
+
+struct HostLineSrc {
+    const uint64_t* lines;  // [102][40] u64
+    void get(int t, int k, Fp2& l0, Fp2& l3k, Fp2& l4k) const {
+        const uint64_t* L = lines + (size_t)t * 40;
+        l0 = load_fp2(L + BN_LINE_OFF_L0 / 2);
+        l3k = load_fp2(L + (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3) / 2);
+        l4k = load_fp2(L + (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4) / 2);
+    }
+};
+
+struct HostLineSink {
+    uint64_t* out;
+    void operator()(int t, const Line& L) {
+        uint64_t* p = out + (size_t)t * 40;
+        store_fp2(p + 0, L.l0);
+        store_fp2(p + 8, L.l3);
+        store_fp2(p + 16, L.xl3);
+        store_fp2(p + 24, L.l4);
+        store_fp2(p + 32, L.xl4);
+    }
+};
+
+Jac<FqOps> load_g1(const uint64_t* p) { return Jac<FqOps>{load_fp(p), load_fp(p + 4), load_fp(p + 8)}; }
+Jac<Fq2Ops> load_g2(const uint64_t* p) { return Jac<Fq2Ops>{load_fp2(p), load_fp2(p + 8), load_fp2(p + 16)}; }
+
+}  // namespace
+
+extern "C" {
+
+// op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 inv(a), 5 half(a), 6 from_mont(a);  which: 0 Fq, 1 Fr
+void emu_fp_op(int op, int which, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    Fp x = load_fp(a), y = b ? load_fp(b) : fp_zero(), r;
+    if (which == 0) {
+        switch (op) {
+            case 0: r = fp_mul<ModQ>(x, y); break;
+            case 1: r = fp_add<ModQ>(x, y); break;
+            case 2: r = fp_sub<ModQ>(x, y); break;
+            case 3: r = fp_neg<ModQ>(x); break;
+            case 4: r = fp_inv<ModQ>(x); break;
+            case 5: r = fp_half<ModQ>(x); break;
+            default: r = fp_from_mont<ModQ>(x); break;
+        }
+    } else {
+        switch (op) {
+            case 0: r = fp_mul<ModR>(x, y); break;
+            case 1: r = fp_add<ModR>(x, y); break;
+            case 2: r = fp_sub<ModR>(x, y); break;
+            case 3: r = fp_neg<ModR>(x); break;
+            case 4: r = fp_inv<ModR>(x); break;
+            case 5: r = fp_half<ModR>(x); break;
+            default: r = fp_from_mont<ModR>(x); break;
+        }
+    }
+    store_fp(out, r);
+}
+// op: 0 mul, 1 sqr, 2 mul_xi, 3 inv, 4 add, 5 sub
+void emu_fp2_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    Fp2 x = load_fp2(a), y = b ? load_fp2(b) : fp2_zero(), r;
+    switch (op) {
+        case 0: r = fp2_mul(x, y); break;
+        case 1: r = fp2_sqr(x); break;
+        case 2: r = fp2_mul_xi(x); break;
+        case 3: r = fp2_inv(x); break;
+        case 4: r = fp2_add(x, y); break;
+        default: r = fp2_sub(x, y); break;
+    }
+    store_fp2(out, r);
+}
+void emu_g1_mul(const uint64_t* p, const uint64_t* fr, uint64_t* out) {
+    Jac<FqOps> r = jac_mul<FqOps>(load_g1(p), load_fp(fr));
+    store_fp(out, r.x); store_fp(out + 4, r.y); store_fp(out + 8, r.z);
+}
+void emu_g2_mul(const uint64_t* p, const uint64_t* fr, uint64_t* out) {
+    Jac<Fq2Ops> r = jac_mul<Fq2Ops>(load_g2(p), load_fp(fr));
+    store_fp2(out, r.x); store_fp2(out + 8, r.y); store_fp2(out + 16, r.z);
+}
+// lines: [102][40] u64.  returns 1 if finite, 0 if either input is infinity.
+int emu_lines(const uint64_t* g1, const uint64_t* g2, uint64_t* lines, uint64_t* p_affine8, uint64_t* q_affine16) {
+    Fp px, py; Fp2 qx, qy;
+    bool ok = pair_to_affine(load_g1(g1), load_g2(g2), px, py, qx, qy);
+    if (p_affine8) { store_fp(p_affine8, px); store_fp(p_affine8 + 4, py); }
+    if (q_affine16) { store_fp2(q_affine16, qx); store_fp2(q_affine16 + 8, qy); }
+    HostLineSink sink{lines};
+    ate_lines(px, py, qx, qy, sink);
+    return ok ? 1 : 0;
+}
+// Gt images are bn::Gt layout (48 u64).  op: 0 mul(a,b) 1 sqr 2 cyc_sqr 3 inv 4 frob(p=arg) 5 exp_by_neg_z
+//   6 final_exp 7 conj 8 pow(a, plain exponent b[0..3])
+void emu_gt_op(int op, const uint64_t* a, const uint64_t* b, int arg, uint64_t* out) {
+    run_hexad([&](HostCtx& c) {
+        Fp2 x = load_fp2(a + 8 * gt_slot(c.k()));
+        Fp2 y = b && op == 0 ? load_fp2(b + 8 * gt_slot(c.k())) : fp2_zero();
+        Fp2 r;
+        switch (op) {
+            case 0: r = hx_mul(c, x, y); break;
+            case 1: r = hx_sqr(c, x); break;
+            case 2: r = hx_cyc_sqr(c, x); break;
+            case 3: r = hx_inv(c, x); break;
+            case 4: r = hx_frob(c, x, arg); break;
+            case 5: r = hx_exp_by_neg_z(c, x); break;
+            case 6: r = hx_final_exp(c, x); break;
+            case 7: r = hx_conj(c, x); break;
+            default: r = hx_pow(c, x, load_fp(b)); break;
+        }
+        store_fp2(out + 8 * gt_slot(c.k()), r);
+    });
+}
+// Miller loop only (unreduced), from stored lines
+void emu_miller(const uint64_t* lines, uint64_t* out) {
+    run_hexad([&](HostCtx& c) {
+        HostLineSrc src{lines};
+        Fp2 f = hx_miller_loop(c, src);
+        store_fp2(out + 8 * gt_slot(c.k()), f);
+    });
+}
+// full pairing through the same code path as the kernels
+void emu_pairing(const uint64_t* g1, const uint64_t* g2, uint64_t* out) {
+    std::vector<uint64_t> lines(102 * 40);
+    int finite = emu_lines(g1, g2, lines.data(), nullptr, nullptr);
+    run_hexad([&](HostCtx& c) {
+        HostLineSrc src{lines.data()};
+        Fp2 f = hx_miller_loop(c, src);
+        f = hx_final_exp(c, f);
+        if (!finite) f = hx_one(c);
+        store_fp2(out + 8 * gt_slot(c.k()), f);
+    });
+}
+}
