@@ -1,0 +1,54 @@
+"""ctypes loader for libbn_b200.so.  Fails loudly: no library or no GPU => exception, never a CPU path."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libbn_b200.so")
+
+EXPORTS = [
+    "bn_b200_init", "bn_b200_shutdown", "bn_b200_last_error", "bn_b200_sm_count",
+    "bn_b200_pairing_batch", "bn_b200_pairing_batch_dev",
+    "bn_b200_g1_mul_batch", "bn_b200_g1_mul_batch_dev", "bn_b200_g2_mul_batch", "bn_b200_g2_mul_batch_dev",
+    "bn_b200_gt_pow_batch", "bn_b200_gt_pow_batch_dev", "bn_b200_gt_mul_batch", "bn_b200_gt_mul_batch_dev",
+    "bn_b200_fq_mul_chain", "bn_b200_fq_mul_chain_dev", "bn_b200_imad_peak_dev",
+    "bn_b200_set_profiling", "bn_b200_last_pairing_kernel_ms", "bn_b200_launch_count",
+]
+
+
+class BnB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library (does not touch the GPU)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise BnB200Error(
+                "%s is missing: build it with `python -m bn_b200.build` (nvcc, sm_100a). "
+                "There is no CPU fallback." % SO_PATH)
+        lib = ctypes.CDLL(SO_PATH)
+        lib.bn_b200_last_error.restype = ctypes.c_char_p
+        lib.bn_b200_launch_count.restype = ctypes.c_ulonglong
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise BnB200Error("bn_b200 error %d: %s" % (rc, load().bn_b200_last_error().decode()))
+
+
+_inited = None
+
+
+def init(device: int = 0):
+    """Bind this process to one CUDA device.  Raises if no device / not sm_100-class."""
+    global _inited
+    if _inited != device:
+        check(load().bn_b200_init(int(device)))
+        _inited = device
+    return load()

@@ -1,0 +1,122 @@
+"""Batch entry points on numpy byte images + thin value classes mirroring reference src/lib.rs.
+
+Byte images are the crate's #[repr(C)] layouts as numpy uint64 arrays:
+  Fr [n,4]   G1 [n,12]   G2 [n,24]   Gt [n,48]      (Montgomery form, LE limbs)
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+FR_WORDS, G1_WORDS, G2_WORDS, GT_WORDS = 4, 12, 24, 48
+
+
+def _arr(a, words):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    if a.shape[-1] != words:
+        raise ValueError("expected [n,%d] uint64 image, got %s" % (words, a.shape))
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _binary(fn_name, a, wa, b, wb, wo, device):
+    lib = _lib.init(device)
+    a, b = _arr(a, wa), _arr(b, wb)
+    if len(a) != len(b):
+        raise ValueError("batch length mismatch")
+    out = np.empty((len(a), wo), dtype=np.uint64)
+    _lib.check(getattr(lib, fn_name)(_p(a), _p(b), _p(out), ctypes.c_size_t(len(a))))
+    return out
+
+
+def pairing_batch(g1, g2, device: int = 0) -> np.ndarray:
+    """[n] pairings e(g1[i], g2[i]) -> Gt images.  reference bn::pairing, src/lib.rs:181-183."""
+    return _binary("bn_b200_pairing_batch", g1, G1_WORDS, g2, G2_WORDS, GT_WORDS, device)
+
+
+def g1_mul_batch(g1, fr, device: int = 0) -> np.ndarray:
+    """g1[i] * fr[i] (Jacobian, un-normalised like the crate).  reference src/lib.rs:116-120."""
+    return _binary("bn_b200_g1_mul_batch", g1, G1_WORDS, fr, FR_WORDS, G1_WORDS, device)
+
+
+def g2_mul_batch(g2, fr, device: int = 0) -> np.ndarray:
+    """reference src/lib.rs:159-163."""
+    return _binary("bn_b200_g2_mul_batch", g2, G2_WORDS, fr, FR_WORDS, G2_WORDS, device)
+
+
+def gt_pow_batch(gt, fr, device: int = 0) -> np.ndarray:
+    """gt[i].pow(fr[i]).  reference Gt::pow, src/lib.rs:171."""
+    return _binary("bn_b200_gt_pow_batch", gt, GT_WORDS, fr, FR_WORDS, GT_WORDS, device)
+
+
+def gt_mul_batch(a, b, device: int = 0) -> np.ndarray:
+    """a[i] * b[i].  reference src/lib.rs:175-179."""
+    return _binary("bn_b200_gt_mul_batch", a, GT_WORDS, b, GT_WORDS, GT_WORDS, device)
+
+
+def fq_mul_chain(a, b, iters: int, device: int = 0) -> np.ndarray:
+    """x <- x*b (Montgomery mod q) `iters` times per element (BASELINE config 2)."""
+    lib = _lib.init(device)
+    a, b = _arr(a, 4), _arr(b, 4)
+    out = np.empty_like(a)
+    _lib.check(lib.bn_b200_fq_mul_chain(_p(a), _p(b), _p(out), ctypes.c_size_t(len(a)), ctypes.c_uint32(iters)))
+    return out
+
+
+class _Img:
+    WORDS = 0
+    __slots__ = ("img",)
+
+    def __init__(self, img):
+        self.img = np.ascontiguousarray(img, dtype=np.uint64).reshape(self.WORDS)
+
+    def __eq__(self, other):  # limb equality (Gt / Fr are canonical; for G1/G2 this is stricter than the crate's projective eq)
+        return type(self) is type(other) and bool(np.array_equal(self.img, other.img))
+
+    def __hash__(self):
+        return hash(self.img.tobytes())
+
+
+class Fr(_Img):
+    """reference src/lib.rs:15-54 (the scalar is carried as its Montgomery image)."""
+    WORDS = FR_WORDS
+
+
+class G1(_Img):
+    """reference src/lib.rs:79-120."""
+    WORDS = G1_WORDS
+
+    def __mul__(self, k: Fr) -> "G1":
+        return G1(g1_mul_batch(self.img[None], k.img[None])[0])
+
+
+class G2(_Img):
+    """reference src/lib.rs:122-163."""
+    WORDS = G2_WORDS
+
+    def __mul__(self, k: Fr) -> "G2":
+        return G2(g2_mul_batch(self.img[None], k.img[None])[0])
+
+
+class Gt(_Img):
+    """reference src/lib.rs:165-179."""
+    WORDS = GT_WORDS
+
+    def pow(self, k: Fr) -> "Gt":
+        return Gt(gt_pow_batch(self.img[None], k.img[None])[0])
+
+    def __mul__(self, other: "Gt") -> "Gt":
+        return Gt(gt_mul_batch(self.img[None], other.img[None])[0])
+
+
+def pairing(p: G1, q: G2) -> Gt:
+    """reference src/lib.rs:181-183."""
+    return Gt(pairing_batch(p.img[None], q.img[None])[0])

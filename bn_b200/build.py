@@ -1,0 +1,40 @@
+"""Build libbn_b200.so (sm_100a only) in-tree with nvcc.  `python -m bn_b200.build [--force]`."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libbn_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550",
+]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc", ".py"))) + [
+        os.path.join(os.path.dirname(HERE), "include", "bn_b200.h")]
+
+
+def is_stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return SO
+    if not (os.path.exists(os.path.join(CSRC, "constants_fp.inc")) and os.path.exists(os.path.join(CSRC, "constants_tower.inc"))):
+        subprocess.check_call([sys.executable, os.path.join(CSRC, "gen_constants.py")])
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(CSRC, "kernels.cu")]
+    subprocess.check_call(cmd, cwd=HERE)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

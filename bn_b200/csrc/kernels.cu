@@ -1,0 +1,469 @@
+// kernels.cu -- sm_100a kernels and the C ABI (include/bn_b200.h) of the batched BN254 engine.
+//
+// Kernel map:
+//   k_fq_mul_chain   K1  Fq Montgomery multiply chain (BASELINE config 2; measures the IMAD roofline)
+//   k_g1_mul/k_g2_mul K3 batched scalar multiplication, one thread per point
+//   k_pair_lines     K4a to_affine (one shared inversion) + the 102 ate lines, one thread per pairing,
+//                        streamed to HBM in consumption order
+//   k_miller_fexp    K4b Miller accumulation + final exponentiation, one 6-lane hexad per pairing
+//                        (5 pairings per warp), all Fq12 state in registers
+//   k_gt_mul/k_gt_pow K5 batched Gt arithmetic on hexads
+// There is no CPU fallback anywhere in this file: without a device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/bn_b200.h"
+#include "pairing.cuh"
+
+using namespace bn;
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fp ld_fp(const uint32_t* p) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    Fp r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fp(uint32_t* p, const Fp& a) {
+    reinterpret_cast<uint4*>(p)[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+__device__ __forceinline__ Fp2 ld_fp2(const uint32_t* p) { return Fp2{ld_fp(p), ld_fp(p + 8)}; }
+__device__ __forceinline__ void st_fp2(uint32_t* p, const Fp2& a) {
+    st_fp(p, a.c0);
+    st_fp(p + 8, a.c1);
+}
+
+struct DevCtx {
+    int kk, base;
+    __device__ __forceinline__ int k() const { return kk; }
+    __device__ __forceinline__ Fp2 shfl(const Fp2& v, int src) const {
+        Fp2 r;
+        const int lane = base + src;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            r.c0.v[i] = __shfl_sync(0xffffffffu, v.c0.v[i], lane);
+            r.c1.v[i] = __shfl_sync(0xffffffffu, v.c1.v[i], lane);
+        }
+        return r;
+    }
+};
+
+// lines live in HBM as [line t][pairing p][80 words]: a warp's five pairings read 5*320 contiguous bytes
+struct DevLineSrc {
+    const uint32_t* base;
+    size_t n, pidx;
+    __device__ __forceinline__ void get(int t, int k, Fp2& l0, Fp2& l3k, Fp2& l4k) const {
+        const uint32_t* L = base + ((size_t)t * n + pidx) * BN_LINE_WORDS;
+        l0 = ld_fp2(L + BN_LINE_OFF_L0);
+        l3k = ld_fp2(L + (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3));
+        l4k = ld_fp2(L + (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4));
+    }
+};
+struct DevLineSink {
+    uint32_t* base;
+    size_t n, pidx;
+    __device__ __forceinline__ void operator()(int t, const Line& L) const {
+        uint32_t* p = base + ((size_t)t * n + pidx) * BN_LINE_WORDS;
+        st_fp2(p + BN_LINE_OFF_L0, L.l0);
+        st_fp2(p + BN_LINE_OFF_L3, L.l3);
+        st_fp2(p + BN_LINE_OFF_XL3, L.xl3);
+        st_fp2(p + BN_LINE_OFF_L4, L.l4);
+        st_fp2(p + BN_LINE_OFF_XL4, L.xl4);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fq_mul_chain(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                                                      uint32_t* __restrict__ out, size_t n, uint32_t iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x = ld_fp(a + i * 8), y = ld_fp(b + i * 8);
+#pragma unroll 2
+    for (uint32_t k = 0; k < iters; k++) x = fp_mul<ModQ>(x, y);
+    st_fp(out + i * 8, x);
+}
+
+// Calibration: nothing but independent IMAD.WIDE.U32 chains (8 accumulator pairs per thread), to measure the
+// fma-pipe integer-multiply issue rate the pairing kernels are bounded by.  32 IMAD.WIDE per loop trip.
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t* __restrict__ out, uint32_t iters, uint32_t seed) {
+    uint64_t acc[8];
+    uint32_t x = threadIdx.x * 2654435761u + seed, y = blockIdx.x * 40503u + 12345u;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = (uint64_t)(x + j) << 7;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(x + (uint32_t)j), "r"(y));
+            y += 0x9e3779b9u;
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= acc[j];
+    if (s == 0x123456789abcdefULL) out[0] = (uint32_t)s;  // practically never: keeps the chain live
+}
+
+__global__ void __launch_bounds__(128) k_g1_mul(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k,
+                                                uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Jac<FqOps> P;
+    P.x = ld_fp(p + i * 24);
+    P.y = ld_fp(p + i * 24 + 8);
+    P.z = ld_fp(p + i * 24 + 16);
+    Jac<FqOps> r = jac_mul<FqOps>(P, ld_fp(k + i * 8));
+    st_fp(out + i * 24, r.x);
+    st_fp(out + i * 24 + 8, r.y);
+    st_fp(out + i * 24 + 16, r.z);
+}
+
+__global__ void __launch_bounds__(128) k_g2_mul(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k,
+                                                uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Jac<Fq2Ops> P;
+    P.x = ld_fp2(p + i * 48);
+    P.y = ld_fp2(p + i * 48 + 16);
+    P.z = ld_fp2(p + i * 48 + 32);
+    Jac<Fq2Ops> r = jac_mul<Fq2Ops>(P, ld_fp(k + i * 8));
+    st_fp2(out + i * 48, r.x);
+    st_fp2(out + i * 48 + 16, r.y);
+    st_fp2(out + i * 48 + 32, r.z);
+}
+
+// K4a: one thread per pairing.  flags[p] = 1 when the pair is finite, 0 when either point is infinity.
+__global__ void __launch_bounds__(64) k_pair_lines(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
+                                                   uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Jac<FqOps> P;
+    P.x = ld_fp(g1 + i * 24);
+    P.y = ld_fp(g1 + i * 24 + 8);
+    P.z = ld_fp(g1 + i * 24 + 16);
+    Jac<Fq2Ops> Q;
+    Q.x = ld_fp2(g2 + i * 48);
+    Q.y = ld_fp2(g2 + i * 48 + 16);
+    Q.z = ld_fp2(g2 + i * 48 + 32);
+    Fp px, py;
+    Fp2 qx, qy;
+    bool finite = pair_to_affine(P, Q, px, py, qx, qy);
+    flags[i] = finite ? 1 : 0;
+    DevLineSink sink{lines, n, i};
+    ate_lines(px, py, qx, qy, sink);
+}
+
+#define HEX_WARPS_PER_BLOCK 4
+#define HEX_PER_WARP 5
+
+struct HexIndex {
+    DevCtx ctx;
+    size_t pidx;   // pairing / element index (clamped to a valid one)
+    bool active;   // this lane belongs to a real element
+};
+__device__ __forceinline__ HexIndex hex_index(size_t n) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int hex = lane / 6;  // 0..5 (5 = the two spare lanes)
+    HexIndex h;
+    h.ctx.kk = lane - hex * 6;
+    h.ctx.base = hex * 6;
+    size_t idx = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP + hex;
+    h.active = (hex < HEX_PER_WARP) && (idx < n);
+    h.pidx = h.active ? idx : (n - 1);
+    return h;
+}
+
+// K4b: Miller loop + final exponentiation, one hexad per pairing.
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
+k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
+    HexIndex h = hex_index(n);
+    DevLineSrc src{lines, n, h.pidx};
+    Fp2 f = hx_miller_loop(h.ctx, src);
+    f = hx_final_exp(h.ctx, f);
+    if (!flags[h.pidx]) f = hx_one(h.ctx);  // infinity => Gt::one(), reference src/groups/mod.rs:765-766
+    if (h.active) st_fp2(out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk), f);
+}
+
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
+k_gt_mul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n) {
+    HexIndex h = hex_index(n);
+    const int slot = 16 * gt_slot(h.ctx.kk);
+    Fp2 x = ld_fp2(a + h.pidx * 96 + slot), y = ld_fp2(b + h.pidx * 96 + slot);
+    Fp2 r = hx_mul(h.ctx, x, y);
+    if (h.active) st_fp2(out + h.pidx * 96 + slot, r);
+}
+
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
+k_gt_pow(const uint32_t* __restrict__ a, const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
+    HexIndex h = hex_index(n);
+    const int slot = 16 * gt_slot(h.ctx.kk);
+    Fp2 x = ld_fp2(a + h.pidx * 96 + slot);
+    Fp e = fp_from_mont<ModR>(ld_fp(k + h.pidx * 8));  // U256::from(Fr), reference src/fields/fp.rs:15-22
+    Fp2 r = hx_pow(h.ctx, x, e);
+    if (h.active) st_fp2(out + h.pidx * 96 + slot, r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: state, error handling, C ABI
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct State {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t* lines = nullptr;
+    size_t lines_cap = 0;  // pairings
+    uint8_t* flags = nullptr;
+    size_t flags_cap = 0;
+    void* stage[3] = {nullptr, nullptr, nullptr};
+    size_t stage_cap[3] = {0, 0, 0};
+    bool profiling = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    cudaStream_t ev_stream = nullptr;
+};
+State g;
+std::mutex g_mu;
+std::atomic<unsigned long long> g_launches{0};
+thread_local std::string t_err;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess)
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else
+        snprintf(buf, sizeof buf, "%s", what);
+    t_err = buf;
+    return code;
+}
+#define CU(call)                                                        \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return fail(BN_B200_ECUDA, #call, e_);   \
+    } while (0)
+
+int ensure_ready() {
+    if (g.ready) return 0;
+    return fail(BN_B200_ENODEV, "bn_b200_init() has not succeeded (no CUDA device bound; there is no CPU fallback)");
+}
+int ensure_buf(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc", e);
+    *cap = bytes;
+    return 0;
+}
+inline unsigned blocks_for(size_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+inline const uint32_t* W(const void* p) { return reinterpret_cast<const uint32_t*>(p); }
+inline uint32_t* W(void* p) { return reinterpret_cast<uint32_t*>(p); }
+
+int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    if (g.lines_cap < n) {
+        if (g.lines) cudaFree(g.lines);
+        g.lines = nullptr;
+        g.lines_cap = 0;
+        cudaError_t e = cudaMalloc(&g.lines, n * (size_t)BN_NUM_LINES * BN_LINE_WORDS * 4);
+        if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc(line buffer)", e);
+        g.lines_cap = n;
+    }
+    int rc = ensure_buf(reinterpret_cast<void**>(&g.flags), &g.flags_cap, n);
+    if (rc) return rc;
+    if (g.profiling) CU(cudaEventRecord(g.ev[0], st));
+    k_pair_lines<<<blocks_for(n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
+    if (g.profiling) CU(cudaEventRecord(g.ev[1], st));
+    k_miller_fexp<<<blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), 32 * HEX_WARPS_PER_BLOCK, 0, st>>>(
+        g.lines, g.flags, W(d_out), n);
+    if (g.profiling) {
+        CU(cudaEventRecord(g.ev[2], st));
+        g.ev_valid = true;
+        g.ev_stream = st;
+    }
+    g_launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// generic "copy in, run the _dev variant, copy out" driver for the host-pointer entry points
+template <class Launch>
+int host_call(const void* a, size_t a_bytes, const void* b, size_t b_bytes, void* out, size_t out_bytes, Launch launch) {
+    int rc;
+    if ((rc = ensure_buf(&g.stage[0], &g.stage_cap[0], a_bytes))) return rc;
+    if ((rc = ensure_buf(&g.stage[1], &g.stage_cap[1], b_bytes))) return rc;
+    if ((rc = ensure_buf(&g.stage[2], &g.stage_cap[2], out_bytes))) return rc;
+    CU(cudaMemcpyAsync(g.stage[0], a, a_bytes, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(g.stage[1], b, b_bytes, cudaMemcpyHostToDevice, g.stream));
+    if ((rc = launch(g.stage[0], g.stage[1], g.stage[2], g.stream))) return rc;
+    CU(cudaMemcpyAsync(out, g.stage[2], out_bytes, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bn_b200_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.ready && g.device == device) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(BN_B200_ENODEV, "no CUDA device visible (this library has no CPU fallback)", e);
+    if (device < 0 || device >= count) return fail(BN_B200_EINVAL, "device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(BN_B200_ENODEV, "device is not sm_100-class; kernels are built for sm_100a only");
+    if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++)
+        if (!g.ev[i]) CU(cudaEventCreate(&g.ev[i]));
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    g.ready = true;
+    return 0;
+}
+
+int bn_b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.ready) return 0;
+    cudaStreamSynchronize(g.stream);
+    if (g.lines) cudaFree(g.lines);
+    if (g.flags) cudaFree(g.flags);
+    for (int i = 0; i < 3; i++) {
+        if (g.stage[i]) cudaFree(g.stage[i]);
+        if (g.ev[i]) cudaEventDestroy(g.ev[i]);
+    }
+    cudaStreamDestroy(g.stream);
+    g = State();
+    return 0;
+}
+
+const char* bn_b200_last_error(void) { return t_err.c_str(); }
+int bn_b200_sm_count(void) { return g.sm_count; }
+unsigned long long bn_b200_launch_count(void) { return g_launches.load(); }
+
+int bn_b200_set_profiling(int enable) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.profiling = enable != 0;
+    g.ev_valid = false;
+    return 0;
+}
+int bn_b200_last_pairing_kernel_ms(float ms[2]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!ms) return fail(BN_B200_EINVAL, "null output");
+    if (!g.ev_valid) return fail(BN_B200_EINVAL, "no profiled pairing call recorded (call bn_b200_set_profiling(1) first)");
+    CU(cudaEventSynchronize(g.ev[2]));
+    CU(cudaEventElapsedTime(&ms[0], g.ev[0], g.ev[1]));
+    CU(cudaEventElapsedTime(&ms[1], g.ev[1], g.ev[2]));
+    return 0;
+}
+
+int bn_b200_pairing_batch_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t n, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n && (!d_p || !d_q || !d_out)) return fail(BN_B200_EINVAL, "null pointer");
+    return pairing_dev_locked(d_p, d_q, d_out, n, stream ? (cudaStream_t)stream : g.stream);
+}
+int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (!p || !q || !out) return fail(BN_B200_EINVAL, "null pointer");
+    return host_call(p, n * sizeof(bn_g1), q, n * sizeof(bn_g2), out, n * sizeof(bn_gt),
+                     [&](void* a, void* b, void* o, cudaStream_t st) {
+                         return pairing_dev_locked((const bn_g1*)a, (const bn_g2*)b, (bn_gt*)o, n, st);
+                     });
+}
+
+#define DEFINE_BINARY(NAME, KERNEL, TA, TB, TO, PER_BLOCK, THREADS)                                              \
+    static int NAME##_launch(const void* a, const void* b, void* o, size_t n, cudaStream_t st) {                  \
+        if (n == 0) return 0;                                                                                     \
+        KERNEL<<<blocks_for(n, PER_BLOCK), THREADS, 0, st>>>(W(a), W(b), W(o), n);                                \
+        g_launches += 1;                                                                                          \
+        CU(cudaGetLastError());                                                                                   \
+        return 0;                                                                                                 \
+    }                                                                                                             \
+    int bn_b200_##NAME##_batch_dev(const TA* d_a, const TB* d_b, TO* d_out, size_t n, void* stream) {             \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                     \
+        int rc = ensure_ready();                                                                                  \
+        if (rc) return rc;                                                                                        \
+        if (n && (!d_a || !d_b || !d_out)) return fail(BN_B200_EINVAL, "null pointer");                           \
+        return NAME##_launch(d_a, d_b, d_out, n, stream ? (cudaStream_t)stream : g.stream);                       \
+    }                                                                                                             \
+    int bn_b200_##NAME##_batch(const TA* a, const TB* b, TO* out, size_t n) {                                     \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                     \
+        int rc = ensure_ready();                                                                                  \
+        if (rc) return rc;                                                                                        \
+        if (n == 0) return 0;                                                                                     \
+        if (!a || !b || !out) return fail(BN_B200_EINVAL, "null pointer");                                        \
+        return host_call(a, n * sizeof(TA), b, n * sizeof(TB), out, n * sizeof(TO),                               \
+                         [&](void* x, void* y, void* o, cudaStream_t st) { return NAME##_launch(x, y, o, n, st); }); \
+    }
+
+DEFINE_BINARY(g1_mul, k_g1_mul, bn_g1, bn_fr, bn_g1, 128, 128)
+DEFINE_BINARY(g2_mul, k_g2_mul, bn_g2, bn_fr, bn_g2, 128, 128)
+DEFINE_BINARY(gt_pow, k_gt_pow, bn_gt, bn_fr, bn_gt, HEX_WARPS_PER_BLOCK* HEX_PER_WARP, 32 * HEX_WARPS_PER_BLOCK)
+DEFINE_BINARY(gt_mul, k_gt_mul, bn_gt, bn_gt, bn_gt, HEX_WARPS_PER_BLOCK* HEX_PER_WARP, 32 * HEX_WARPS_PER_BLOCK)
+
+static int fq_chain_launch(const void* a, const void* b, void* o, size_t n, uint32_t iters, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_fq_mul_chain<<<blocks_for(n, 256), 256, 0, st>>>(W(a), W(b), W(o), n, iters);
+    g_launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+int bn_b200_fq_mul_chain_dev(const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n, uint32_t iters, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n && (!d_a || !d_b || !d_out)) return fail(BN_B200_EINVAL, "null pointer");
+    return fq_chain_launch(d_a, d_b, d_out, n, iters, stream ? (cudaStream_t)stream : g.stream);
+}
+int bn_b200_fq_mul_chain(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, uint32_t iters) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (!a || !b || !out) return fail(BN_B200_EINVAL, "null pointer");
+    return host_call(a, n * 32, b, n * 32, out, n * 32, [&](void* x, void* y, void* o, cudaStream_t st) {
+        return fq_chain_launch(x, y, o, n, iters, st);
+    });
+}
+
+/* calibration: run `blocks` x 256 threads of pure IMAD.WIDE.U32 (32 per loop trip, `iters` trips) on `stream`. */
+int bn_b200_imad_peak_dev(uint32_t* d_scratch, uint32_t blocks, uint32_t iters, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!d_scratch) return fail(BN_B200_EINVAL, "null pointer");
+    k_imad_peak<<<blocks, 256, 0, stream ? (cudaStream_t)stream : g.stream>>>(d_scratch, iters, 1u);
+    g_launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+/*
+ * bn_b200.h -- C ABI of the B200-native batched BN254 engine (libbn_b200.so).
+ *
+ * This is the drop-in boundary for the `bn` crate (zcash-hackworks/bn): every struct below is
+ * byte-identical to the crate's #[repr(C)] public type, so `&[G1]`, `&[G2]`, `&mut [Gt]` cross the FFI as
+ * raw pointers with no marshalling.  All field elements are Montgomery form (x * 2^256 mod p), canonical
+ * in [0, p), four little-endian u64 limbs -- exactly what the crate keeps in memory
+ * (reference src/arith.rs:9-11, src/fields/fp.rs:11-13).
+ *
+ * The reference has no FFI of its own; each entry point names the public Rust item it replaces.
+ * INTEGRATION.md shows the `extern "C"` block and the thin Rust wrappers a maintainer would add.
+ *
+ * Conventions
+ *   - return 0 on success, a negative BN_B200_E* code on failure; never unwinds, never aborts;
+ *     bn_b200_last_error() gives a message for the last failure on the calling thread.
+ *   - caller owns every buffer; the library owns its stream, scratch memory and events.
+ *   - host-pointer entry points copy H2D, run the kernels and copy D2H before returning.
+ *   - *_dev entry points take DEVICE pointers (same layouts) and enqueue on `stream`
+ *     (a cudaStream_t cast to void*; NULL = the library's own stream) without synchronising.
+ *   - thread-safe: calls are serialised by an internal lock (the crate's types are Send + Sync,
+ *     reference src/lib.rs:56-66).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with BN_B200_ENODEV.
+ */
+#ifndef BN_B200_H
+#define BN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } bn_fr;                          /* bn::Fr  src/lib.rs:15-17     32 B */
+typedef struct { uint64_t x[4], y[4], z[4]; } bn_g1;              /* bn::G1  src/lib.rs:79-81     96 B, Jacobian */
+typedef struct { uint64_t x[2][4], y[2][4], z[2][4]; } bn_g2;     /* bn::G2  src/lib.rs:122-124  192 B, Fq2 = c0 then c1 */
+typedef struct { uint64_t c[2][3][2][4]; } bn_gt;                 /* bn::Gt  src/lib.rs:165-167  384 B, Fq12.c{0,1}.c{0,1,2}.c{0,1} */
+
+#define BN_B200_OK 0
+#define BN_B200_ENODEV (-1)   /* no CUDA device / driver */
+#define BN_B200_ECUDA (-2)    /* a CUDA runtime call failed */
+#define BN_B200_EINVAL (-3)   /* null pointer or bad argument */
+#define BN_B200_ENOMEM (-4)   /* device allocation failed */
+
+/* Select the CUDA device for this process (one process per GPU), create the stream. Idempotent. */
+int bn_b200_init(int device);
+int bn_b200_shutdown(void);
+const char* bn_b200_last_error(void);
+/* Number of SMs of the active device (0 before init). */
+int bn_b200_sm_count(void);
+
+/* pairing(p, q) for n independent pairs.              replaces bn::pairing, src/lib.rs:181-183
+ * (groups::pairing src/groups/mod.rs:764-771: to_affine + precompute + miller_loop + final_exponentiation;
+ *  either input at infinity => Gt::one()). */
+int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n);
+int bn_b200_pairing_batch_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t n, void* stream);
+
+/* out[i] = p[i] * k[i].                               replaces `impl Mul<Fr> for G1/G2`, src/lib.rs:116-120, 159-163
+ * Output is the same un-normalised Jacobian triple the crate produces (src/groups/mod.rs:250-270). */
+int bn_b200_g1_mul_batch(const bn_g1* p, const bn_fr* k, bn_g1* out, size_t n);
+int bn_b200_g1_mul_batch_dev(const bn_g1* d_p, const bn_fr* d_k, bn_g1* d_out, size_t n, void* stream);
+int bn_b200_g2_mul_batch(const bn_g2* p, const bn_fr* k, bn_g2* out, size_t n);
+int bn_b200_g2_mul_batch_dev(const bn_g2* d_p, const bn_fr* d_k, bn_g2* d_out, size_t n, void* stream);
+
+/* out[i] = a[i].pow(k[i]).                            replaces Gt::pow, src/lib.rs:171 (FieldElement::pow, src/fields/mod.rs:35-46) */
+int bn_b200_gt_pow_batch(const bn_gt* a, const bn_fr* k, bn_gt* out, size_t n);
+int bn_b200_gt_pow_batch_dev(const bn_gt* d_a, const bn_fr* d_k, bn_gt* d_out, size_t n, void* stream);
+/* out[i] = a[i] * b[i].                               replaces `impl Mul<Gt> for Gt`, src/lib.rs:175-179 */
+int bn_b200_gt_mul_batch(const bn_gt* a, const bn_gt* b, bn_gt* out, size_t n);
+int bn_b200_gt_mul_batch_dev(const bn_gt* d_a, const bn_gt* d_b, bn_gt* d_out, size_t n, void* stream);
+
+/* x <- x * b (Montgomery, mod q) repeated `iters` times per element: the BASELINE config-2 microbenchmark of
+ * the innermost operation (Fq Mul, src/fields/fp.rs:137-146 -> U256::mul src/arith.rs:257-263). a, b, out: n x 4 u64. */
+int bn_b200_fq_mul_chain(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, uint32_t iters);
+int bn_b200_fq_mul_chain_dev(const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n, uint32_t iters, void* stream);
+
+/* Calibration kernel for the roofline denominator: `blocks` x 256 threads each issue iters*32 independent
+ * IMAD.WIDE.U32 (the instruction every Fq product is made of).  d_scratch: >= 4 bytes of device memory. */
+int bn_b200_imad_peak_dev(uint32_t* d_scratch, uint32_t blocks, uint32_t iters, void* stream);
+
+/* Per-kernel device timing of the most recent pairing_batch[_dev] call, measured with CUDA events on the
+ * stream the kernels were launched on (enable first; reading synchronises that stream).
+ * ms[0] = line-schedule kernel, ms[1] = Miller-loop + final-exponentiation kernel. */
+int bn_b200_set_profiling(int enable);
+int bn_b200_last_pairing_kernel_ms(float ms[2]);
+/* Number of kernels this library has launched since init (for the bench's gpu_launches claim). */
+unsigned long long bn_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BN_B200_H */

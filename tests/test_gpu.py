@@ -1,0 +1,168 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI
+(libbn_b200.so via bn_b200/_lib.py) and is compared bit-for-bit with the oracle on the same inputs.
+Mirrors the reference's tests: test_reduced_pairing / test_binlinearity (src/groups/mod.rs:773-823),
+group_trials (src/groups/tests.rs), golden vectors (tests/serialization.rs)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import bn_oracle as o
+from oracle import cref
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bn():
+    import bn_b200
+    bn_b200.init(0)
+    return bn_b200
+
+
+def test_fq_mul_chain(bn):
+    a = util.synth_scalars(0xB2000002, 300)
+    b = util.synth_scalars(0xB2000012, 300)
+    a[0] = 0
+    b[1] = util.words((o.Q - 1).to_bytes(32, "little"))
+    for iters in (1, 7, 100):
+        assert np.array_equal(bn.fq_mul_chain(a, b, iters), cref.fq_mul_chain(a, b, iters, 4)), iters
+
+
+def test_pairing_kat(bn):
+    kat = util.load_json("pairing_kat.json")
+    g1 = cref.g1_mul_batch(cref.g1_generator(), util.fr_img(int(kat["k1"]))[None])
+    g2 = cref.g2_mul_batch(cref.g2_generator(), util.fr_img(int(kat["k2"]))[None])
+    gt = bn.pairing_batch(g1, g2)
+    assert np.array_equal(gt[0], util.gt_img(o.fq12_from_flat(kat["reduced_pairing"])))
+    # value-class mirror of the crate API
+    assert bn.pairing(bn.G1(g1[0]), bn.G2(g2[0])) == bn.Gt(gt[0])
+
+
+def test_pairing_edge_cases(bn):
+    g1, g2 = util.edge_case_pairs()
+    assert np.array_equal(bn.pairing_batch(g1, g2), cref.pairing_batch(g1, g2))
+    one = util.gt_img(o.FQ12_ONE)
+    got = bn.pairing_batch(g1, g2)
+    for i in (1, 2, 4, 5):
+        assert np.array_equal(got[i], one)
+
+
+@pytest.mark.parametrize("n", [1, 4, 5, 6, 19, 20, 21, 257])
+def test_pairing_ragged_batches(bn, n):
+    g1, g2 = util.synth_pairs(0xB2000001 + n, n)
+    assert np.array_equal(bn.pairing_batch(g1, g2), cref.pairing_batch(g1, g2, 8))
+
+
+def test_pairing_config1_1024(bn):
+    """BASELINE config 1: 1024 random pairs, Gt bit-exact vs the CPU oracle (with edge cases mixed in)."""
+    g1, g2 = util.synth_pairs(0xB2000001, 1024)
+    e1, e2 = util.edge_case_pairs()
+    g1[100:100 + len(e1)] = e1
+    g2[100:100 + len(e2)] = e2
+    assert np.array_equal(bn.pairing_batch(g1, g2), cref.pairing_batch(g1, g2, 8))
+    assert bn.pairing_batch(np.zeros((0, 12), np.uint64), np.zeros((0, 24), np.uint64)).shape == (0, 48)
+
+
+def test_scalar_mul_limb_exact(bn):
+    n = 200
+    g1, g2 = util.synth_pairs(0xB2000003, n)
+    k = util.synth_scalars(0xB2000013, n)
+    for i, s in enumerate([0, 1, 2, o.R_ORDER - 1, 23938123]):
+        k[i] = util.fr_img(s)
+    g1[10] = util.g1_img(o.g_zero(o.FQ))
+    g2[11] = util.g2_img(o.g_zero(o.FQ2))
+    g1[12] = cref.g1_generator()[0]
+    g2[12] = cref.g2_generator()[0]
+    assert np.array_equal(bn.g1_mul_batch(g1, k), cref.g1_mul_batch(g1, k, 8))
+    assert np.array_equal(bn.g2_mul_batch(g2, k), cref.g2_mul_batch(g2, k, 8))
+
+
+def test_g1_golden_vectors(bn):
+    """tests/serialization.rs g1_vectors recurrence acc <- acc*23938123 + acc; the GPU does the scalar mul."""
+    lines = util.load_vectors("g1_vectors.txt", 60)
+    k = util.fr_img(23938123)[None]
+    acc = cref.g1_generator()
+    for want in lines:
+        assert o.encode_g1(util.img_g1(cref.g1_normalize(acc)[0])).hex() == want
+        acc = cref.g1_add(bn.g1_mul_batch(acc, k), acc)
+
+
+def test_g2_golden_vectors(bn):
+    lines = util.load_vectors("g2_vectors.txt", 25)
+    k = util.fr_img(23938123)[None]
+    acc = cref.g2_generator()
+    for want in lines:
+        assert o.encode_g2(util.img_g2(cref.g2_normalize(acc)[0])).hex() == want
+        acc = cref.g2_add(bn.g2_mul_batch(acc, k), acc)
+
+
+def test_gt_mul_pow(bn):
+    n = 23
+    g1, g2 = util.synth_pairs(77, n)
+    gt = cref.pairing_batch(g1, g2, 8)
+    k = util.synth_scalars(78, n)
+    for i, s in enumerate([0, 1, 2, o.R_ORDER - 1]):
+        k[i] = util.fr_img(s)
+    assert np.array_equal(bn.gt_mul_batch(gt, gt[::-1].copy()), cref.gt_mul_batch(gt, gt[::-1].copy(), 8))
+    assert np.array_equal(bn.gt_pow_batch(gt, k), cref.gt_pow_batch(gt, k, 8))
+    # non-cyclotomic operand
+    f = util.load_json("fq12_kat.json")
+    s = util.gt_img(o.fq12_from_flat(f["vector_start"]))[None]
+    assert np.array_equal(bn.gt_mul_batch(s, s), cref.fq12_mul(s, s))
+    assert np.array_equal(bn.gt_pow_batch(s, k[5:6]), cref.gt_pow_batch(s, k[5:6]))
+
+
+def test_bilinearity_on_gpu(bn):
+    """test_binlinearity (src/groups/mod.rs:798-823) entirely on the GPU: e(P,Q)^s == e(sP,Q) == e(P,sQ)."""
+    n = 64
+    g1, g2 = util.synth_pairs(5, n)
+    s = util.synth_scalars(6, n)
+    a = bn.gt_pow_batch(bn.pairing_batch(g1, g2), s)
+    b = bn.pairing_batch(bn.g1_mul_batch(g1, s), g2)
+    c = bn.pairing_batch(g1, bn.g2_mul_batch(g2, s))
+    assert np.array_equal(a, b) and np.array_equal(b, c)
+    one = util.gt_img(o.FQ12_ONE)
+    m1 = np.repeat(util.fr_img(o.R_ORDER - 1)[None], n, axis=0)
+    assert all(np.array_equal(x, one) for x in bn.gt_mul_batch(bn.gt_pow_batch(a, m1), a))
+    assert not any(np.array_equal(x, one) for x in a)
+
+
+def test_full_size_config4_properties(bn):
+    """BASELINE config 4 size (2^14): the oracle cannot finish this in seconds, so check size-independent
+    properties: a sampled subset is bit-exact vs the oracle, and e(P, Q)*e(-P, Q) == 1 for every pair."""
+    n = 1 << 14
+    gen1, gen2 = cref.g1_generator(), cref.g2_generator()
+    a = util.synth_scalars(0xB2000004, n)
+    b = util.synth_scalars(0xB2000014, n)
+    g1 = bn.g1_mul_batch(np.repeat(gen1, n, axis=0), a)   # on-device input generation (row f-2)
+    g2 = bn.g2_mul_batch(np.repeat(gen2, n, axis=0), b)
+    gt = bn.pairing_batch(g1, g2)
+    idx = np.arange(0, n, n // 64)
+    assert np.array_equal(gt[idx], cref.pairing_batch(g1[idx], g2[idx], 8))
+    neg = g1.copy()
+    q = np.frombuffer(o.Q.to_bytes(32, "little"), dtype="<u8")
+    # -P: y -> q - y on the Montgomery limbs (y != 0 for points of odd order)
+    y = [int.from_bytes(r.tobytes(), "little") for r in g1[:, 4:8]]
+    neg[:, 4:8] = np.stack([util.words((o.Q - v).to_bytes(32, "little")) for v in y])
+    prod = bn.gt_mul_batch(gt, bn.pairing_batch(neg, g2))
+    one = util.gt_img(o.FQ12_ONE)
+    assert (prod == one[None]).all()
+
+
+def test_device_pointer_api_with_torch(bn):
+    import torch
+    n = 40
+    g1, g2 = util.synth_pairs(9, n)
+    t1 = torch.from_numpy(g1.view(np.int64)).cuda()
+    t2 = torch.from_numpy(g2.view(np.int64)).cuda()
+    out = torch.empty((n, 48), dtype=torch.int64, device="cuda")
+    lib = bn.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.bn_b200_pairing_batch_dev(ctypes.c_void_p(t1.data_ptr()), ctypes.c_void_p(t2.data_ptr()),
+                                       ctypes.c_void_p(out.data_ptr()), ctypes.c_size_t(n), ctypes.c_void_p(st))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), cref.pairing_batch(g1, g2, 8))
+    assert lib.bn_b200_launch_count() >= 2

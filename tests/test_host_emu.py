@@ -1,0 +1,132 @@
+"""CPU tests: the kernels' arithmetic (bn_b200/csrc/*.cuh) compiled for the host -- PTX chains swapped for
+their portable equivalents, warp shuffles for a six-thread barrier exchange -- against the oracle.
+This validates the tower formulas, the hexad lane choreography and the line schedule without a GPU;
+the -m gpu tests validate the real kernels through the C ABI."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bn_oracle as o
+from oracle import cref
+from tests import emu, util
+
+rnd = random.Random(20260925)
+
+
+def _int(a):
+    return int.from_bytes(np.asarray(a, dtype="<u8").tobytes(), "little")
+
+
+def _w(x):
+    return util.words(x.to_bytes(32, "little"))
+
+
+def fq2img(a):
+    return util.words(o.fq2_to_bytes(a))
+
+
+@pytest.mark.parametrize("which,p", [(0, o.Q), (1, o.R_ORDER)])
+def test_fp_ops(which, p):
+    rinv = pow(o.MONT_R, -1, p)
+    specials = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, 2**253, 2**32 - 1, (2**256 - 1) % p]
+    vals = specials + [rnd.randrange(p) for _ in range(150)]
+    for a in vals:
+        b = rnd.choice(vals)
+        assert _int(emu.fp_op(0, which, _w(a), _w(b))) == a * b * rinv % p
+        assert _int(emu.fp_op(1, which, _w(a), _w(b))) == (a + b) % p
+        assert _int(emu.fp_op(2, which, _w(a), _w(b))) == (a - b) % p
+        assert _int(emu.fp_op(3, which, _w(a))) == (-a) % p
+        assert _int(emu.fp_op(5, which, _w(a))) == a * pow(2, -1, p) % p
+        assert _int(emu.fp_op(6, which, _w(a))) == a * rinv % p
+    for a in [1, 2, p - 1] + [rnd.randrange(1, p) for _ in range(6)]:
+        assert _int(emu.fp_op(4, which, _w(a))) == pow(a * rinv % p, -1, p) * o.MONT_R % p
+
+
+def test_fp2_ops():
+    edge = [(0, 0), (o.Q - 1, o.Q - 1), (5, 0), (0, o.Q - 1), (1, 1)]
+    for i in range(120):
+        a = edge[i % 5] if i < 10 else (rnd.randrange(o.Q), rnd.randrange(o.Q))
+        b = edge[(i // 2) % 5] if i < 10 else (rnd.randrange(o.Q), rnd.randrange(o.Q))
+        assert np.array_equal(emu.fp2_op(0, fq2img(a), fq2img(b)), fq2img(o.fq2_mul(a, b)))
+        assert np.array_equal(emu.fp2_op(1, fq2img(a)), fq2img(o.fq2_sqr(a)))
+        assert np.array_equal(emu.fp2_op(2, fq2img(a)), fq2img(o.fq2_mul_xi(a)))
+        if a != (0, 0):
+            assert np.array_equal(emu.fp2_op(3, fq2img(a)), fq2img(o.fq2_inv(a)))
+
+
+@pytest.fixture(scope="module")
+def pairs():
+    g1, g2 = util.synth_pairs(3, 4)
+    return g1, g2, cref.pairing_batch(g1, g2, 4)
+
+
+def test_scalar_mul_limb_exact(pairs):
+    g1, g2, _ = pairs
+    ks = [o.synth_scalar(4, 0), 0, 1, o.R_ORDER - 1]
+    for i, k in enumerate(ks):
+        fr = util.fr_img(k)
+        assert np.array_equal(emu.g1_mul(g1[i], fr), cref.g1_mul_batch(g1[i:i + 1], fr[None])[0])
+        assert np.array_equal(emu.g2_mul(g2[i], fr), cref.g2_mul_batch(g2[i:i + 1], fr[None])[0])
+
+
+def test_line_schedule_matches_precompute(pairs):
+    g1, g2, _ = pairs
+    finite, L, pa, qa = emu.lines(g1[0], g2[0])
+    assert finite == 1
+    P = o.g_to_affine(o.FQ, util.img_g1(g1[0]))
+    Qa = o.g_to_affine(o.FQ2, util.img_g2(g2[0]))
+    assert np.array_equal(pa, np.concatenate([util.words(o.fq_to_bytes(P[0])), util.words(o.fq_to_bytes(P[1]))]))
+    assert np.array_equal(qa, np.concatenate([fq2img(Qa[0]), fq2img(Qa[1])]))
+    co = o.g2_precompute(Qa)
+    for t, (e0, evw, evv) in enumerate(co):
+        l3 = o.fq2_scale(evw, P[1])
+        l4 = o.fq2_scale(evv, P[0])
+        exp = np.concatenate([fq2img(e0), fq2img(l3), fq2img(o.fq2_mul_xi(l3)), fq2img(l4), fq2img(o.fq2_mul_xi(l4))])
+        assert np.array_equal(L[t], exp), t
+    assert np.array_equal(emu.miller(L), util.gt_img(o.miller_loop(co, P)))
+
+
+def test_hexad_fq12_ops(pairs):
+    _, _, gt = pairs
+    a, b = gt[0], gt[1]
+    assert np.array_equal(emu.gt_op(0, a, b), cref.fq12_mul(a[None], b[None])[0])
+    assert np.array_equal(emu.gt_op(1, a), cref.fq12_sqr(a[None])[0])
+    assert np.array_equal(emu.gt_op(2, a), util.gt_img(o.fq12_cyclotomic_squared(util.img_gt(a))))
+    assert np.array_equal(emu.gt_op(3, a), cref.fq12_inv(a[None])[0])
+    assert np.array_equal(emu.gt_op(7, a), util.gt_img(o.fq12_conj(util.img_gt(a))))
+    for p in (1, 2, 3):
+        assert np.array_equal(emu.gt_op(4, a, arg=p), cref.fq12_frobenius(a[None], p)[0])
+    assert np.array_equal(emu.gt_op(5, a), cref.fq12_exp_by_neg_z(a[None])[0])
+    # generic (non-cyclotomic) element: the reference's fq12_test_vector start value
+    f = util.load_json("fq12_kat.json")
+    s = util.gt_img(o.fq12_from_flat(f["vector_start"]))
+    nxt = s
+    for _ in range(5):
+        nxt = emu.gt_op(0, nxt, s)
+    nxt = emu.gt_op(1, nxt)
+    want = util.img_gt(s)
+    acc = want
+    for _ in range(5):
+        acc = o.fq12_mul(acc, want)
+    assert np.array_equal(nxt, util.gt_img(o.fq12_sqr(acc)))
+    assert np.array_equal(emu.gt_op(3, s), util.gt_img(o.fq12_inv(want)))
+    k = o.synth_scalar(9, 0)
+    assert np.array_equal(emu.gt_op(8, a, _w(k)), cref.gt_pow_batch(a[None], util.fr_img(k)[None])[0])
+
+
+def test_pairing_kat_and_random(pairs):
+    g1, g2, gt = pairs
+    kat = util.load_json("pairing_kat.json")
+    kg1 = cref.g1_mul_batch(cref.g1_generator(), util.fr_img(int(kat["k1"]))[None])[0]
+    kg2 = cref.g2_mul_batch(cref.g2_generator(), util.fr_img(int(kat["k2"]))[None])[0]
+    assert np.array_equal(emu.pairing(kg1, kg2), util.gt_img(o.fq12_from_flat(kat["reduced_pairing"])))
+    for i in range(len(g1)):
+        assert np.array_equal(emu.pairing(g1[i], g2[i]), gt[i])
+
+
+def test_pairing_edge_cases():
+    e1, e2 = util.edge_case_pairs()
+    egt = cref.pairing_batch(e1, e2)
+    for i in range(len(e1)):
+        assert np.array_equal(emu.pairing(e1[i], e2[i]), egt[i]), i
