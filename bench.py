@@ -135,7 +135,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 256 * max(1, min(cores, 64) // 4)
+    sample = 128 * cores
     rates, times = [], []
     for i in range(args.warmup + args.steps):
         r, dt = cpu_reference_rate(sample, cores)
@@ -190,7 +190,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     n = args.pairs
-    stream = torch.cuda.current_stream()
+    # An explicit (non-default) stream: the default stream's handle is NULL, which the C ABI maps to the library's
+    # own stream -- torch events would then not see the kernels.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     sp = ctypes.c_void_p(stream.cuda_stream)
 
     def dptr(t):
@@ -322,7 +326,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = 256 * max(1, min(cores, 64) // 4)
+        sample = 128 * cores
         rate, dt = cpu_reference_rate(sample, cores)
         rate1, dt1 = cpu_reference_rate(128, 1)
         cpu = {"value": rate, "unit": "pairings/s", "cores": cores, "kind": "port",

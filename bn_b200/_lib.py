@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbn_b200.so")
+SO_PATH = os.environ.get("BN_B200_SO") or os.path.join(_HERE, "libbn_b200.so")  # env override: A/B builds only
 
 EXPORTS = [
     "bn_b200_init", "bn_b200_shutdown", "bn_b200_last_error", "bn_b200_sm_count",

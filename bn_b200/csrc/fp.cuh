@@ -513,6 +513,91 @@ BN_HD void wide_dbl(Wide& acc) {
     acc.w[0] <<= 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Carry-save 512-bit accumulator: products keep accumulating in the (E, O) limb arrays across MANY
+// multiply-accumulates; the carry out of every 4-IMAD chain goes to a small per-position counter instead of
+// rippling through limbs that already hold data.  One merge (E + 2^32 O + counters) per reduction.
+// Saves the two 16-limb merges per product pair that Wide/wide_mac2 pay.
+// ------------------------------------------------------------------------------------------------
+struct AccEO {
+    uint32_t E[16];
+    uint32_t O[16];   // O[15] stays 0
+    uint32_t CE[4];   // carries into E positions 8,10,12,14
+    uint32_t CO[4];   // carries into O positions 8,10,12,14
+};
+BN_HD void acc_zero(AccEO& a) {
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) { a.E[i] = 0; a.O[i] = 0; }
+    BN_UNROLL
+    for (int i = 0; i < 4; i++) { a.CE[i] = 0; a.CO[i] = 0; }
+}
+// chain with the carry-out going to a separate counter register
+BN_HD void mad_row4_cs(uint32_t* acc, uint32_t& counter, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "+r"(counter)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+#else
+    uint32_t t[9];
+    for (int j = 0; j < 8; j++) t[j] = acc[j];
+    t[8] = counter;
+    mad_row4(t, x0, x1, x2, x3, y);
+    for (int j = 0; j < 8; j++) acc[j] = t[j];
+    counter = t[8];
+#endif
+}
+// acc += a * b
+BN_HD void acc_mac(AccEO& A, const Fp& a, const Fp& b) {
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) {
+        const uint32_t y = b.v[i];
+        if ((i & 1) == 0) {
+            // even row: E window [i, i+8) -> carry to E position i+8 ; O window [i, i+8) -> carry to O position i+8
+            if (i + 8 < 16) {
+                mad_row4_cs(&A.E[i], A.CE[i / 2], a.v[0], a.v[2], a.v[4], a.v[6], y);
+                mad_row4_cs(&A.O[i], A.CO[i / 2], a.v[1], a.v[3], a.v[5], a.v[7], y);
+            }
+        } else {
+            // odd row: O window [i-1, i+7) -> carry to O position i+7 ; E window [i+1, i+9) -> carry to E position i+9
+            mad_row4_cs(&A.O[i - 1], A.CO[(i - 1) / 2], a.v[0], a.v[2], a.v[4], a.v[6], y);
+            if (i + 9 < 16)
+                mad_row4_cs(&A.E[i + 1], A.CE[(i + 1) / 2], a.v[1], a.v[3], a.v[5], a.v[7], y);
+            else
+                mad_row4_nc(&A.E[i + 1], a.v[1], a.v[3], a.v[5], a.v[7], y);  // top window: total < 2^512, no carry out
+        }
+    }
+}
+// merge to a plain 512-bit integer
+BN_HD Wide acc_merge(const AccEO& A) {
+    Wide T;
+    uint32_t e_hi[8], o_hi[8];
+    // fold the counters into the high halves (positions 8,10,12,14)
+    const uint32_t ce[8] = {A.CE[0], 0u, A.CE[1], 0u, A.CE[2], 0u, A.CE[3], 0u};
+    const uint32_t co[8] = {A.CO[0], 0u, A.CO[1], 0u, A.CO[2], 0u, A.CO[3], 0u};
+    (void)add8(e_hi, &A.E[8], ce);
+    (void)add8(o_hi, &A.O[8], co);
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) T.w[i] = A.E[i];
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) T.w[8 + i] = e_hi[i];
+    uint32_t o_all[16];
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) o_all[i] = A.O[i];
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) o_all[8 + i] = o_hi[i];
+    add16_shift1(T.w, o_all);
+    return T;
+}
+
 // Montgomery reduction: returns T / 2^256 mod p, in [0, T/2^256 + p).  Caller applies cond_sub.
 // Word-serial (HAC 14.32, as reference src/arith.rs:497-500) on the low half only; T's high half is
 // added at the end so each chain's carry lands in a fresh limb.  64 IMAD.WIDE + 8 IMAD.

@@ -26,13 +26,15 @@ namespace bn {
 // acc0 + acc1 i += x * y.  LAZY=false: y canonical (y1 negated as q - y1, each product < q^2);
 // LAZY=true: components of x, y < 2q (y1 negated as 2q - y1, each product < 4 q^2).
 template <bool LAZY>
-BN_HD void mac_fp2(Wide& acc0, Wide& acc1, const Fp2& x, const Fp2& y) {
+BN_HD void mac_fp2(AccEO& acc0, AccEO& acc1, const Fp2& x, const Fp2& y) {
     Fp ny1 = LAZY ? fp_neg_2q(y.c1) : fp_neg_lazy<MQ>(y.c1);
-    wide_mac2(acc0, x.c0, y.c0, x.c1, ny1);
-    wide_mac2(acc1, x.c0, y.c1, x.c1, y.c0);
+    acc_mac(acc0, x.c0, y.c0);
+    acc_mac(acc0, x.c1, ny1);
+    acc_mac(acc1, x.c0, y.c1);
+    acc_mac(acc1, x.c1, y.c0);
 }
-BN_HD Fp2 reduce2(const Wide& acc0, const Wide& acc1) {
-    return Fp2{mont_reduce<MQ, 4>(acc0), mont_reduce<MQ, 4>(acc1)};
+BN_HD Fp2 reduce2(const AccEO& acc0, const AccEO& acc1) {
+    return Fp2{mont_reduce<MQ, 4>(acc_merge(acc0)), mont_reduce<MQ, 4>(acc_merge(acc1))};
 }
 BN_HD int nib(uint32_t packed, int k) { return (int)((packed >> (4 * k)) & 7u); }
 BN_HD int mod6(int x) { return x >= 6 ? x - 6 : x; }
@@ -54,7 +56,9 @@ template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul(const Ctx& c, const Fp2& a, const Fp2& b) {
     const int k = c.k();
     Fp2 xa = fp2_mul_xi(a);
-    Wide acc0 = wide_zero(), acc1 = wide_zero();
+    AccEO acc0, acc1;
+    acc_zero(acc0);
+    acc_zero(acc1);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -69,27 +73,27 @@ BN_HD_NOINLINE Fp2 hx_mul(const Ctx& c, const Fp2& a, const Fp2& b) {
 }
 
 // square.  reference src/fields/fq12.rs:275-282.  21 distinct products in 4 lock-step rounds:
-//   rounds 1-2: cross terms (doubled afterwards on the 512-bit accumulators)
-//   round 3   : even lanes a_i^2, odd lanes their third cross term (sender pre-doubles)
+//   rounds 1-2: cross terms (the sender ships 2 a_i or 2 xi a_i)
+//   round 3   : even lanes a_i^2, odd lanes their third cross term
 //   round 4   : even lanes xi * a_j^2, odd lanes idle
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_sqr(const Ctx& c, const Fp2& a) {
     const int k = c.k();
     Fp2 xa = fp2_mul_xi(a);
-    Fp2 d = fp2_dbl(fp2_select(k == 4, xa, a));  // lane 3 sends 2 a_3, lane 4 sends 2 xi a_4 in round 3
-    Wide acc0 = wide_zero(), acc1 = wide_zero();
-    {   // round 1: lane0: xi a5 * a1 ; lane k>0: a0 * a_k
-        Fp2 x = c.shfl(fp2_select(k == 5, xa, a), nib(0x000005u, k));
+    Fp2 d = fp2_dbl(fp2_select(k >= 4, xa, a));  // doubled operand: 2 a_k on lanes 0..3, 2 xi a_k on lanes 4,5
+    AccEO acc0, acc1;
+    acc_zero(acc0);
+    acc_zero(acc1);
+    {   // round 1 (cross terms, sender pre-doubles): lane0: (2 xi a5) a1 ; lane k>0: (2 a0) a_k
+        Fp2 x = c.shfl(d, nib(0x000005u, k));
         Fp2 y = c.shfl(a, nib(0x543211u, k));
         mac_fp2<false>(acc0, acc1, x, y);
     }
-    {   // round 2: xi a4 a2 | xi a5 a2 | xi a5 a3 | a1 a2 | a1 a3 | a1 a4
-        Fp2 x = c.shfl(fp2_select(k >= 4, xa, a), nib(0x111554u, k));
+    {   // round 2: 2xi a4 a2 | 2xi a5 a2 | 2xi a5 a3 | 2 a1 a2 | 2 a1 a3 | 2 a1 a4
+        Fp2 x = c.shfl(d, nib(0x111554u, k));
         Fp2 y = c.shfl(a, nib(0x432322u, k));
         mac_fp2<false>(acc0, acc1, x, y);
     }
-    wide_dbl(acc0);
-    wide_dbl(acc1);
     {   // round 3: a0 a0 | (2 xi a4) a3 | a1 a1 | (2 xi a4) a5 | a2 a2 | (2 a3) a2
         Fp2 x = c.shfl(fp2_select(k == 3 || k == 4, d, a), nib(0x324140u, k));
         Fp2 y = c.shfl(a, nib(0x225130u, k));
@@ -101,7 +105,7 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx& c, const Fp2& a) {
         y = fp2_select((k & 1) != 0, fp2_zero(), y);
         mac_fp2<false>(acc0, acc1, x, y);
     }
-    return reduce2(acc0, acc1);  // < (2+2)*2 + 2 + 2 = 12 q^2
+    return reduce2(acc0, acc1);  // 4 rounds * 2 q^2 per accumulator
 }
 
 // product with the sparse line l0 + l3 w^3 + l4 w^4 (reference mul_by_024, src/fields/fq12.rs:107-176).
@@ -109,7 +113,9 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx& c, const Fp2& a) {
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx& c, const Fp2& a, const Fp2& l0, const Fp2& l3k, const Fp2& l4k) {
     const int k = c.k();
-    Wide acc0 = wide_zero(), acc1 = wide_zero();
+    AccEO acc0, acc1;
+    acc_zero(acc0);
+    acc_zero(acc1);
     mac_fp2<false>(acc0, acc1, a, l0);
     Fp2 x3 = c.shfl(a, mod6(k + 3));  // a_{k-3}
     mac_fp2<false>(acc0, acc1, x3, l3k);
@@ -124,7 +130,9 @@ BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx& c, const Fp2& a, const Fp2& m0, const F
     const int k = c.k();
     Fp2 m1k = fp2_select(k < 2, fp2_mul_xi(m1), m1);
     Fp2 m2k = fp2_select(k < 4, fp2_mul_xi(m2), m2);
-    Wide acc0 = wide_zero(), acc1 = wide_zero();
+    AccEO acc0, acc1;
+    acc_zero(acc0);
+    acc_zero(acc1);
     mac_fp2<false>(acc0, acc1, a, m0);
     Fp2 x2 = c.shfl(a, mod6(k + 4));  // a_{k-2}
     mac_fp2<false>(acc0, acc1, x2, m1k);
@@ -160,7 +168,9 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx& c, const Fp2& a) {
     f0.c1 = fp_add_raw(x.c1, fp_select(pre, y.c1, fp_zero()));
     f1.c0 = fp_add_raw(fp_select(pre, xy.c0, y.c0), fp_select(pre, x.c0, fp_zero()));
     f1.c1 = fp_add_raw(fp_select(pre, xy.c1, y.c1), fp_select(pre, x.c1, fp_zero()));
-    Wide acc0 = wide_zero(), acc1 = wide_zero();
+    AccEO acc0, acc1;
+    acc_zero(acc0);
+    acc_zero(acc1);
     mac_fp2<true>(acc0, acc1, f0, f1);  // < 8 q^2
     Fp2 r = reduce2(acc0, acc1);
     // partner product: lane0 <- lane3, lane2 <- lane5, lane4 <- lane1

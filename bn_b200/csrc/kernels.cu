@@ -99,22 +99,20 @@ __global__ void __launch_bounds__(256) k_fq_mul_chain(const uint32_t* __restrict
 // fma-pipe integer-multiply issue rate the pairing kernels are bounded by.  32 IMAD.WIDE per loop trip.
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* __restrict__ out, uint32_t iters, uint32_t seed) {
     uint64_t acc[8];
-    uint32_t x = threadIdx.x * 2654435761u + seed, y = blockIdx.x * 40503u + 12345u;
+    const uint32_t y = blockIdx.x * 40503u + 12345u + seed;
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = (uint64_t)(x + j) << 7;
+    for (int j = 0; j < 8; j++) acc[j] = ((uint64_t)(threadIdx.x * 2654435761u + j) << 7) | 1u;
     for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(x + (uint32_t)j), "r"(y));
-            y += 0x9e3779b9u;
+            for (int j = 0; j < 8; j++) acc[j] = (uint64_t)(uint32_t)acc[j] * y + acc[j];  // IMAD.WIDE.U32 Rd, Rd.lo, y, Rd
         }
     }
     uint64_t s = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) s ^= acc[j];
-    if (s == 0x123456789abcdefULL) out[0] = (uint32_t)s;  // practically never: keeps the chain live
+    if (s == 0x123456789abcdefULL) out[0] = (uint32_t)s;  // practically never: keeps the chains live
 }
 
 __global__ void __launch_bounds__(128) k_g1_mul(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k,
@@ -166,8 +164,13 @@ __global__ void __launch_bounds__(64) k_pair_lines(const uint32_t* __restrict__ 
     ate_lines(px, py, qx, qy, sink);
 }
 
+#ifndef HEX_WARPS_PER_BLOCK
 #define HEX_WARPS_PER_BLOCK 4
+#endif
 #define HEX_PER_WARP 5
+#ifndef HEX_MIN_BLOCKS
+#define HEX_MIN_BLOCKS 1   // blocks/SM promised to ptxas for the hexad kernels (register cap = 65536 / (threads * blocks))
+#endif
 
 struct HexIndex {
     DevCtx ctx;
@@ -188,7 +191,7 @@ __device__ __forceinline__ HexIndex hex_index(size_t n) {
 }
 
 // K4b: Miller loop + final exponentiation, one hexad per pairing.
-__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
 k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
     HexIndex h = hex_index(n);
     DevLineSrc src{lines, n, h.pidx};

@@ -1,0 +1,29 @@
+#!/bin/bash
+# Run on the GPU box (via gpurun): parity tests, then bench for each library variant, then ncu captures.
+# usage: tools/gpu_ab.sh "<variant .so names or 'default'>" [ncu]
+mkdir -p gpurun_out
+VARIANTS="$1"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+for v in $VARIANTS; do
+  if [ "$v" = "default" ]; then unset BN_B200_SO; else export BN_B200_SO=$PWD/bn_b200/$v; fi
+  extra="--no-cpu-baseline"; [ "$v" = "default" ] && extra=""
+  timeout 600 python bench.py --steps 8 --warmup 3 $extra > gpurun_out/bench_$v.log 2>gpurun_out/bench_$v.err; echo "rc=$?" >> gpurun_out/bench_$v.err
+  python - "$v" <<'PY'
+import json,sys
+v=sys.argv[1]
+try:
+    d=json.loads(open('gpurun_out/bench_%s.log'%v).read().strip().splitlines()[-1])
+    r=d['roofline']
+    print(v,'value %.0f e2e %.0f ms/step %.3f lines %.3f ms miller %.3f ms imad_peak %.2f T frac %.3f whole %.3f fqmul %.3e (%.2f) clocks %s'%(d['value'],d['e2e']['value'],d['ms_per_step'],r['kernel_ms']['k_pair_lines'],r['kernel_ms']['k_miller_fexp'],r['peak'],r['frac'],r['whole_path_frac'],r['fq_mul_chain']['fq_mul_per_s'],r['fq_mul_chain']['imad_frac'],d['clocks']))
+except Exception as e:
+    print(v,'FAILED',e); print(open('gpurun_out/bench_%s.err'%v).read()[-1500:])
+PY
+done
+unset BN_B200_SO
+if [ "$2" = "ncu" ]; then
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_miller_fexp -s 2 -c 1 -o gpurun_out/prof_miller python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_miller.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_pair_lines -s 2 -c 1 -o gpurun_out/prof_lines python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_lines.log 2>&1
+  ls -la gpurun_out/
+fi

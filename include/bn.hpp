@@ -1,0 +1,104 @@
+// bn.hpp -- header-only C++ host layer over the C ABI (bn_b200.h), mirroring the `bn` crate's public API.
+//
+// The reference's host language is Rust; rustc/cargo are not available in the build image, so the host side
+// above the C ABI is written in C++ (the Rust shim a maintainer would add is in INTEGRATION.md).  Names,
+// argument meaning and error behaviour follow reference src/lib.rs:
+//
+//   bn::Fr                     src/lib.rs:15-54      (carried as its Montgomery image; arithmetic stays on the host crate)
+//   bn::G1, bn::G2  operator*  src/lib.rs:79-163     `impl Mul<Fr>`
+//   bn::Gt  pow(), operator*   src/lib.rs:165-179
+//   bn::pairing(G1, G2) -> Gt  src/lib.rs:181-183
+//
+// plus the batch forms the GPU exists for (pairing_batch, mul_batch, pow_batch).  Semantic "errors" do not
+// exist on this path (infinity => Gt::one(), like src/groups/mod.rs:765-766); infrastructure failures (no GPU,
+// CUDA error) throw bn::Error -- there is no CPU fallback.
+#pragma once
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bn_b200.h"
+
+namespace bn {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+    if (rc != 0) throw Error(rc, std::string("bn_b200: ") + bn_b200_last_error());
+}
+inline void init(int device = 0) { check(bn_b200_init(device)); }
+
+struct Fr {
+    bn_fr v;
+    bool operator==(const Fr& o) const { return std::memcmp(&v, &o.v, sizeof v) == 0; }
+};
+struct G1 {
+    bn_g1 v;
+};
+struct G2 {
+    bn_g2 v;
+};
+struct Gt {
+    bn_gt v;
+    bool operator==(const Gt& o) const { return std::memcmp(&v, &o.v, sizeof v) == 0; }
+    bool operator!=(const Gt& o) const { return !(*this == o); }
+    Gt pow(const Fr& k) const {  // Gt::pow, src/lib.rs:171
+        Gt r;
+        check(bn_b200_gt_pow_batch(&v, &k.v, &r.v, 1));
+        return r;
+    }
+};
+static_assert(sizeof(Fr) == 32 && sizeof(G1) == 96 && sizeof(G2) == 192 && sizeof(Gt) == 384,
+              "layouts must match the crate's #[repr(C)] types");
+
+inline G1 operator*(const G1& p, const Fr& k) {  // src/lib.rs:116-120
+    G1 r;
+    check(bn_b200_g1_mul_batch(&p.v, &k.v, &r.v, 1));
+    return r;
+}
+inline G2 operator*(const G2& p, const Fr& k) {  // src/lib.rs:159-163
+    G2 r;
+    check(bn_b200_g2_mul_batch(&p.v, &k.v, &r.v, 1));
+    return r;
+}
+inline Gt operator*(const Gt& a, const Gt& b) {  // src/lib.rs:175-179
+    Gt r;
+    check(bn_b200_gt_mul_batch(&a.v, &b.v, &r.v, 1));
+    return r;
+}
+inline Gt pairing(const G1& p, const G2& q) {  // src/lib.rs:181-183
+    Gt r;
+    check(bn_b200_pairing_batch(&p.v, &q.v, &r.v, 1));
+    return r;
+}
+
+// ---- batch forms: one call, one H2D / kernels / D2H round trip ----
+inline std::vector<Gt> pairing_batch(const std::vector<G1>& p, const std::vector<G2>& q) {
+    if (p.size() != q.size()) throw Error(BN_B200_EINVAL, "pairing_batch: length mismatch");
+    std::vector<Gt> out(p.size());
+    check(bn_b200_pairing_batch(&p.data()->v, &q.data()->v, &out.data()->v, p.size()));
+    return out;
+}
+inline std::vector<G1> mul_batch(const std::vector<G1>& p, const std::vector<Fr>& k) {
+    if (p.size() != k.size()) throw Error(BN_B200_EINVAL, "mul_batch: length mismatch");
+    std::vector<G1> out(p.size());
+    check(bn_b200_g1_mul_batch(&p.data()->v, &k.data()->v, &out.data()->v, p.size()));
+    return out;
+}
+inline std::vector<G2> mul_batch(const std::vector<G2>& p, const std::vector<Fr>& k) {
+    if (p.size() != k.size()) throw Error(BN_B200_EINVAL, "mul_batch: length mismatch");
+    std::vector<G2> out(p.size());
+    check(bn_b200_g2_mul_batch(&p.data()->v, &k.data()->v, &out.data()->v, p.size()));
+    return out;
+}
+inline std::vector<Gt> pow_batch(const std::vector<Gt>& a, const std::vector<Fr>& k) {
+    if (a.size() != k.size()) throw Error(BN_B200_EINVAL, "pow_batch: length mismatch");
+    std::vector<Gt> out(a.size());
+    check(bn_b200_gt_pow_batch(&a.data()->v, &k.data()->v, &out.data()->v, a.size()));
+    return out;
+}
+
+}  // namespace bn
