@@ -10,6 +10,7 @@
 // HBM in the order the Miller kernel consumes them, already multiplied by P's coordinates and by xi where
 // a lane of the Miller kernel needs the wrapped coefficient.  (The reference keeps them in a heap Vec.)
 #pragma once
+#include "duo.cuh"
 #include "fp2.cuh"
 
 namespace bn {
@@ -135,61 +136,82 @@ struct Line {
 #define BN_LINE_WORDS 80
 #define BN_NUM_LINES 102
 
-BN_HD Line make_line(const Fp2& ell_0, const Fp2& ell_vw, const Fp2& ell_vv, const Fp& px, const Fp& py) {
+// Fq2 multiplication policies for the line schedule: one thread per pairing, or a lane pair per pairing (duo.cuh).
+struct SoloX {
+    BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const { return fp2_mul(a, b); }
+    BN_HD Fp2 sqr(const Fp2& a) const { return fp2_sqr(a); }
+    BN_HD Fp2 mul_fp(const Fp2& a, const Fp& k) const { return fp2_mul_fp(a, k); }
+    BN_HD Fp2 mul_xi(const Fp2& a) const { return fp2_mul_xi(a); }
+};
+template <class D>
+struct DuoX {
+    D d;
+    BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const { return duo_mul(d, a, b); }
+    BN_HD Fp2 sqr(const Fp2& a) const { return duo_sqr(d, a); }
+    BN_HD Fp2 mul_fp(const Fp2& a, const Fp& k) const { return duo_mul_fp(d, a, k); }
+    BN_HD Fp2 mul_xi(const Fp2& a) const { return duo_mul_xi(d, a); }
+};
+
+template <class X>
+BN_HD Line make_line(const X& X_, const Fp2& ell_0, const Fp2& ell_vw, const Fp2& ell_vv, const Fp& px, const Fp& py) {
     Line L;
     L.l0 = ell_0;
-    L.l3 = fp2_mul_fp(ell_vw, py);
-    L.l4 = fp2_mul_fp(ell_vv, px);
-    L.xl3 = fp2_mul_xi(L.l3);
-    L.xl4 = fp2_mul_xi(L.l4);
+    L.l3 = X_.mul_fp(ell_vw, py);
+    L.l4 = X_.mul_fp(ell_vv, px);
+    L.xl3 = X_.mul_xi(L.l3);
+    L.xl4 = X_.mul_xi(L.l4);
     return L;
 }
 
 // reference src/groups/mod.rs:612-634
-BN_HD_NOINLINE Line line_double(G2Proj& r, const Fp& px, const Fp& py) {
-    Fp2 a = fp2_half(fp2_mul(r.x, r.y));
-    Fp2 b = fp2_sqr(r.y);
-    Fp2 c = fp2_sqr(r.z);
+template <class X>
+BN_HD_NOINLINE Line line_double(const X& X_, G2Proj& r, const Fp& px, const Fp& py) {
+    Fp2 a = fp2_half(X_.mul(r.x, r.y));
+    Fp2 b = X_.sqr(r.y);
+    Fp2 c = X_.sqr(r.z);
     Fp2 d = fp2_add(fp2_add(c, c), c);
-    Fp2 e = fp2_mul(g2_coeff_b(), d);
+    Fp2 e = X_.mul(g2_coeff_b(), d);
     Fp2 f = fp2_add(fp2_add(e, e), e);
     Fp2 g = fp2_half(fp2_add(b, f));
-    Fp2 h = fp2_sub(fp2_sqr(fp2_add(r.y, r.z)), fp2_add(b, c));
+    Fp2 h = fp2_sub(X_.sqr(fp2_add(r.y, r.z)), fp2_add(b, c));
     Fp2 i = fp2_sub(e, b);
-    Fp2 j = fp2_sqr(r.x);
-    Fp2 e_sq = fp2_sqr(e);
-    r.x = fp2_mul(a, fp2_sub(b, f));
-    r.y = fp2_sub(fp2_sqr(g), fp2_add(fp2_add(e_sq, e_sq), e_sq));
-    r.z = fp2_mul(b, h);
-    return make_line(fp2_mul_xi(i), fp2_neg(h), fp2_add(fp2_add(j, j), j), px, py);
+    Fp2 j = X_.sqr(r.x);
+    Fp2 e_sq = X_.sqr(e);
+    r.x = X_.mul(a, fp2_sub(b, f));
+    r.y = fp2_sub(X_.sqr(g), fp2_add(fp2_add(e_sq, e_sq), e_sq));
+    r.z = X_.mul(b, h);
+    return make_line(X_, X_.mul_xi(i), fp2_neg(h), fp2_add(fp2_add(j, j), j), px, py);
 }
 
 // reference src/groups/mod.rs:592-610
-BN_HD_NOINLINE Line line_add(G2Proj& r, const Fp2& bx, const Fp2& by, const Fp& px, const Fp& py) {
-    Fp2 d = fp2_sub(r.x, fp2_mul(r.z, bx));
-    Fp2 e = fp2_sub(r.y, fp2_mul(r.z, by));
-    Fp2 f = fp2_sqr(d);
-    Fp2 g = fp2_sqr(e);
-    Fp2 h = fp2_mul(d, f);
-    Fp2 i = fp2_mul(r.x, f);
-    Fp2 j = fp2_sub(fp2_add(fp2_mul(r.z, g), h), fp2_add(i, i));
-    r.x = fp2_mul(d, j);
-    r.y = fp2_sub(fp2_mul(e, fp2_sub(i, j)), fp2_mul(h, r.y));
-    r.z = fp2_mul(r.z, h);
-    Fp2 ell_0 = fp2_mul_xi(fp2_sub(fp2_mul(e, bx), fp2_mul(d, by)));
-    return make_line(ell_0, d, fp2_neg(e), px, py);
+template <class X>
+BN_HD_NOINLINE Line line_add(const X& X_, G2Proj& r, const Fp2& bx, const Fp2& by, const Fp& px, const Fp& py) {
+    Fp2 d = fp2_sub(r.x, X_.mul(r.z, bx));
+    Fp2 e = fp2_sub(r.y, X_.mul(r.z, by));
+    Fp2 f = X_.sqr(d);
+    Fp2 g = X_.sqr(e);
+    Fp2 h = X_.mul(d, f);
+    Fp2 i = X_.mul(r.x, f);
+    Fp2 j = fp2_sub(fp2_add(X_.mul(r.z, g), h), fp2_add(i, i));
+    r.x = X_.mul(d, j);
+    r.y = fp2_sub(X_.mul(e, fp2_sub(i, j)), X_.mul(h, r.y));
+    r.z = X_.mul(r.z, h);
+    Fp2 ell_0 = X_.mul_xi(fp2_sub(X_.mul(e, bx), X_.mul(d, by)));
+    return make_line(X_, ell_0, d, fp2_neg(e), px, py);
 }
 
 // twisted Frobenius: reference src/groups/mod.rs:550-555
-BN_HD void g2_mul_by_q(Fp2& x, Fp2& y) {
-    x = fp2_mul(FROB_GAMMA_C[0][2], fp2_conj(x));
-    y = fp2_mul(FROB_GAMMA_C[0][3], fp2_conj(y));
+template <class X>
+BN_HD void g2_mul_by_q(const X& X_, Fp2& x, Fp2& y) {
+    x = X_.mul(FROB_GAMMA_C[0][2], fp2_conj(x));
+    y = X_.mul(FROB_GAMMA_C[0][3], fp2_conj(y));
 }
 
 // Affine coordinates of a (G1, G2) pair with ONE field inversion for both points
 // (reference to_affine, src/groups/mod.rs:113-130, inverts P.z and Q.z separately; the values are the same).
 // Returns false when either point is the point at infinity (pairing = one, src/groups/mod.rs:765-766).
-BN_HD bool pair_to_affine(const Jac<FqOps>& P, const Jac<Fq2Ops>& Q, Fp& px, Fp& py, Fp2& qx, Fp2& qy) {
+template <class X>
+BN_HD bool pair_to_affine(const X& X_, const Jac<FqOps>& P, const Jac<Fq2Ops>& Q, Fp& px, Fp& py, Fp2& qx, Fp2& qy) {
     bool inf = fp_is_zero(P.z) || fp2_is_zero(Q.z);
     Wide n = wide_zero();
     wide_mac2(n, Q.z.c0, Q.z.c0, Q.z.c1, Q.z.c1);
@@ -202,32 +224,32 @@ BN_HD bool pair_to_affine(const Jac<FqOps>& P, const Jac<Fq2Ops>& Q, Fp& px, Fp&
     Fp pz2 = fp_mul<MQ>(pzinv, pzinv);
     px = fp_mul<MQ>(P.x, pz2);
     py = fp_mul<MQ>(P.y, fp_mul<MQ>(pz2, pzinv));
-    Fp2 qz2 = fp2_sqr(qzinv);
-    qx = fp2_mul(Q.x, qz2);
-    qy = fp2_mul(Q.y, fp2_mul(qz2, qzinv));
+    Fp2 qz2 = X_.sqr(qzinv);
+    qx = X_.mul(Q.x, qz2);
+    qy = X_.mul(Q.y, X_.mul(qz2, qzinv));
     return !inf;
 }
 
 // Emit the 102 lines for affine (P, Q) in Miller-loop order.  sink(index, line).
 // reference precompute, src/groups/mod.rs:557-588
-template <class Sink>
-BN_HD void ate_lines(const Fp& px, const Fp& py, const Fp2& qx, const Fp2& qy, Sink& sink) {
+template <class X, class Sink>
+BN_HD void ate_lines(const X& X_, const Fp& px, const Fp& py, const Fp2& qx, const Fp2& qy, Sink& sink) {
     G2Proj r;
     r.x = qx;
     r.y = qy;
     r.z = fp2_one();
     int n = 0;
     for (int b = BN_ATE_NBITS - 1; b >= 0; b--) {
-        sink(n++, line_double(r, px, py));
-        if ((BN_ATE_BITS >> b) & 1ULL) sink(n++, line_add(r, qx, qy, px, py));
+        sink(n++, line_double(X_, r, px, py));
+        if ((BN_ATE_BITS >> b) & 1ULL) sink(n++, line_add(X_, r, qx, qy, px, py));
     }
     Fp2 q1x = qx, q1y = qy;
-    g2_mul_by_q(q1x, q1y);
+    g2_mul_by_q(X_, q1x, q1y);
     Fp2 q2x = q1x, q2y = q1y;
-    g2_mul_by_q(q2x, q2y);
+    g2_mul_by_q(X_, q2x, q2y);
     q2y = fp2_neg(q2y);
-    sink(n++, line_add(r, q1x, q1y, px, py));
-    sink(n++, line_add(r, q2x, q2y, px, py));
+    sink(n++, line_add(X_, r, q1x, q1y, px, py));
+    sink(n++, line_add(X_, r, q2x, q2y, px, py));
 }
 
 }  // namespace bn

@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -158,10 +159,65 @@ __global__ void __launch_bounds__(64) k_pair_lines(const uint32_t* __restrict__ 
     Q.z = ld_fp2(g2 + i * 48 + 32);
     Fp px, py;
     Fp2 qx, qy;
-    bool finite = pair_to_affine(P, Q, px, py, qx, qy);
+    SoloX X_;
+    bool finite = pair_to_affine(X_, P, Q, px, py, qx, qy);
     flags[i] = finite ? 1 : 0;
     DevLineSink sink{lines, n, i};
-    ate_lines(px, py, qx, qy, sink);
+    ate_lines(X_, px, py, qx, qy, sink);
+}
+
+// K4a, lane-pair form (duo.cuh): lanes (2j, 2j+1) compute the lines of one pairing, one Fq2 output component each.
+struct DevDuo {
+    int hh;
+    __device__ __forceinline__ int h() const { return hh; }
+    __device__ __forceinline__ Fp swap(const Fp& v) const {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, v.v[i], 1);
+        return r;
+    }
+};
+struct DevDuoLineSink {
+    uint32_t* base;
+    size_t n, pidx;
+    int h;
+    bool active;
+    // both lanes hold the whole line; lane 0 stores words [0,40), lane 1 stores [40,80)
+    __device__ __forceinline__ void operator()(int t, const Line& L) const {
+        if (!active) return;
+        uint32_t* p = base + ((size_t)t * n + pidx) * BN_LINE_WORDS;
+        if (h == 0) {
+            st_fp2(p + BN_LINE_OFF_L0, L.l0);
+            st_fp2(p + BN_LINE_OFF_L3, L.l3);
+            st_fp(p + BN_LINE_OFF_XL3, L.xl3.c0);
+        } else {
+            st_fp(p + BN_LINE_OFF_XL3 + 8, L.xl3.c1);
+            st_fp2(p + BN_LINE_OFF_L4, L.l4);
+            st_fp2(p + BN_LINE_OFF_XL4, L.xl4);
+        }
+    }
+};
+__global__ void __launch_bounds__(64) k_pair_lines_duo(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
+                                                       uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = t >> 1;
+    const bool active = i < n;
+    if (!active) i = n - 1;  // keep whole warps alive for the shuffles
+    Jac<FqOps> P;
+    P.x = ld_fp(g1 + i * 24);
+    P.y = ld_fp(g1 + i * 24 + 8);
+    P.z = ld_fp(g1 + i * 24 + 16);
+    Jac<Fq2Ops> Q;
+    Q.x = ld_fp2(g2 + i * 48);
+    Q.y = ld_fp2(g2 + i * 48 + 16);
+    Q.z = ld_fp2(g2 + i * 48 + 32);
+    DuoX<DevDuo> X_{DevDuo{(int)(t & 1)}};
+    Fp px, py;
+    Fp2 qx, qy;
+    bool finite = pair_to_affine(X_, P, Q, px, py, qx, qy);
+    if (active && (t & 1) == 0) flags[i] = finite ? 1 : 0;
+    DevDuoLineSink sink{lines, n, i, (int)(t & 1), active};
+    ate_lines(X_, px, py, qx, qy, sink);
 }
 
 #ifndef HEX_WARPS_PER_BLOCK
@@ -237,6 +293,7 @@ struct State {
     void* stage[3] = {nullptr, nullptr, nullptr};
     size_t stage_cap[3] = {0, 0, 0};
     bool profiling = false;
+    bool lines_duo = true;  // line kernel mapping: lane pair per pairing (default) or one thread per pairing
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
     cudaStream_t ev_stream = nullptr;
@@ -292,7 +349,10 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t 
     int rc = ensure_buf(reinterpret_cast<void**>(&g.flags), &g.flags_cap, n);
     if (rc) return rc;
     if (g.profiling) CU(cudaEventRecord(g.ev[0], st));
-    k_pair_lines<<<blocks_for(n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
+    if (g.lines_duo)
+        k_pair_lines_duo<<<blocks_for(2 * n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
+    else
+        k_pair_lines<<<blocks_for(n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
     if (g.profiling) CU(cudaEventRecord(g.ev[1], st));
     k_miller_fexp<<<blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), 32 * HEX_WARPS_PER_BLOCK, 0, st>>>(
         g.lines, g.flags, W(d_out), n);
@@ -340,6 +400,7 @@ int bn_b200_init(int device) {
     if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++)
         if (!g.ev[i]) CU(cudaEventCreate(&g.ev[i]));
+    if (const char* e = getenv("BN_B200_LINES")) g.lines_duo = strcmp(e, "solo") != 0;  // A/B switch, both are bit-exact
     g.device = device;
     g.sm_count = prop.multiProcessorCount;
     g.ready = true;

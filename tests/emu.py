@@ -67,6 +67,14 @@ def lines(g1, g2):
     return finite, out, pa, qa
 
 
+def lines_duo(g1, g2):
+    g1, g2 = _c(g1), _c(g2)
+    o0 = np.zeros((102, 40), dtype=np.uint64)
+    o1 = np.zeros((102, 40), dtype=np.uint64)
+    finite = lib().emu_lines_duo(_p(g1), _p(g2), _p(o0), _p(o1))
+    return finite, o0, o1
+
+
 def gt_op(op, a, b=None, arg=0):
     a, b = _c(a), _c(b)
     out = np.zeros(48, dtype=np.uint64)

@@ -37,6 +37,23 @@ struct HostHexShared {
     Barrier bar{6};
 };
 
+struct HostDuoShared {
+    Fp slot[2];
+    Barrier bar{2};
+};
+struct HostDuo {
+    int hh;
+    HostDuoShared* sh;
+    int h() const { return hh; }
+    Fp swap(const Fp& v) const {
+        sh->slot[hh] = v;
+        sh->bar.wait();
+        Fp r = sh->slot[hh ^ 1];
+        sh->bar.wait();
+        return r;
+    }
+};
+
 struct HostCtx {
     int kk;
     HostHexShared* sh;
@@ -155,12 +172,30 @@ void emu_g2_mul(const uint64_t* p, const uint64_t* fr, uint64_t* out) {
 // lines: [102][40] u64.  returns 1 if finite, 0 if either input is infinity.
 int emu_lines(const uint64_t* g1, const uint64_t* g2, uint64_t* lines, uint64_t* p_affine8, uint64_t* q_affine16) {
     Fp px, py; Fp2 qx, qy;
-    bool ok = pair_to_affine(load_g1(g1), load_g2(g2), px, py, qx, qy);
+    SoloX X_;
+    bool ok = pair_to_affine(X_, load_g1(g1), load_g2(g2), px, py, qx, qy);
     if (p_affine8) { store_fp(p_affine8, px); store_fp(p_affine8 + 4, py); }
     if (q_affine16) { store_fp2(q_affine16, qx); store_fp2(q_affine16 + 8, qy); }
     HostLineSink sink{lines};
-    ate_lines(px, py, qx, qy, sink);
+    ate_lines(X_, px, py, qx, qy, sink);
     return ok ? 1 : 0;
+}
+// same, computed by a lane PAIR (duo.cuh): two host threads; each writes its own copy, both must agree
+int emu_lines_duo(const uint64_t* g1, const uint64_t* g2, uint64_t* lines_lane0, uint64_t* lines_lane1) {
+    HostDuoShared sh;
+    int ok[2] = {0, 0};
+    uint64_t* outs[2] = {lines_lane0, lines_lane1};
+    std::vector<std::thread> th;
+    for (int h = 0; h < 2; h++)
+        th.emplace_back([&, h]() {
+            DuoX<HostDuo> X_{HostDuo{h, &sh}};
+            Fp px, py; Fp2 qx, qy;
+            ok[h] = pair_to_affine(X_, load_g1(g1), load_g2(g2), px, py, qx, qy) ? 1 : 0;
+            HostLineSink sink{outs[h]};
+            ate_lines(X_, px, py, qx, qy, sink);
+        });
+    for (auto& t : th) t.join();
+    return ok[0] & ok[1];
 }
 // Gt images are bn::Gt layout (48 u64).  op: 0 mul(a,b) 1 sqr 2 cyc_sqr 3 inv 4 frob(p=arg) 5 exp_by_neg_z
 //   6 final_exp 7 conj 8 pow(a, plain exponent b[0..3])

@@ -87,6 +87,18 @@ def test_line_schedule_matches_precompute(pairs):
     assert np.array_equal(emu.miller(L), util.gt_img(o.miller_loop(co, P)))
 
 
+def test_duo_line_schedule_equals_solo(pairs):
+    """duo.cuh: the lane-pair line kernel produces the same 102 lines on both lanes as the one-thread version."""
+    g1, g2, _ = pairs
+    e1, e2 = util.edge_case_pairs()
+    for a, b in [(g1[0], g2[0]), (g1[1], g2[1]), (e1[0], e2[0]), (e1[6], e2[6]), (e1[1], e2[1])]:
+        finite, L, _, _ = emu.lines(a, b)
+        f2, L0, L1 = emu.lines_duo(a, b)
+        assert finite == f2
+        if finite:
+            assert np.array_equal(L, L0) and np.array_equal(L, L1)
+
+
 def test_hexad_fq12_ops(pairs):
     _, _, gt = pairs
     a, b = gt[0], gt[1]

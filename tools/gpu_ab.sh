@@ -5,9 +5,12 @@ mkdir -p gpurun_out
 VARIANTS="$1"
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
-for v in $VARIANTS; do
+for spec in $VARIANTS; do
+  v=${spec%%:*}; lines=${spec##*:}; [ "$lines" = "$spec" ] && lines=duo
+  export BN_B200_LINES=$lines
   if [ "$v" = "default" ]; then unset BN_B200_SO; else export BN_B200_SO=$PWD/bn_b200/$v; fi
-  extra="--no-cpu-baseline"; [ "$v" = "default" ] && extra=""
+  extra="--no-cpu-baseline"; [ "$spec" = "default" ] && extra=""
+  v=${v}_$lines
   timeout 600 python bench.py --steps 8 --warmup 3 $extra > gpurun_out/bench_$v.log 2>gpurun_out/bench_$v.err; echo "rc=$?" >> gpurun_out/bench_$v.err
   python - "$v" <<'PY'
 import json,sys
@@ -20,7 +23,7 @@ except Exception as e:
     print(v,'FAILED',e); print(open('gpurun_out/bench_%s.err'%v).read()[-1500:])
 PY
 done
-unset BN_B200_SO
+unset BN_B200_SO BN_B200_LINES
 if [ "$2" = "ncu" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:k_miller_fexp -s 2 -c 1 -o gpurun_out/prof_miller python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_miller.log 2>&1
