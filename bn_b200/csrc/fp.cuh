@@ -26,7 +26,7 @@
 #define BN_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define BN_HD inline
-#define BN_HD_NOINLINE
+#define BN_HD_NOINLINE inline
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -290,6 +290,41 @@ BN_HD uint32_t addi8c(uint32_t* acc, const uint32_t* b, uint32_t cin) {
     return c;
 }
 
+// acc[0..7] -= b[0..7] (- bin); returns borrow-out (0/1).  In place.
+BN_HD uint32_t subi8b(uint32_t* acc, const uint32_t* b, uint32_t bin) {
+    uint32_t bo = bin;
+#if defined(__CUDA_ARCH__)
+    asm("sub.cc.u32 %8, 0, %8;\n\t"  // CF(borrow) = (bin != 0); bin in {0,1}
+        "subc.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, %10;\n\t"
+        "subc.cc.u32 %2, %2, %11;\n\t"
+        "subc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\t"
+        "subc.cc.u32 %5, %5, %14;\n\t"
+        "subc.cc.u32 %6, %6, %15;\n\t"
+        "subc.cc.u32 %7, %7, %16;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "+r"(bo)
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    bo &= 1u;
+#else
+    int64_t t = -(int64_t)bin;
+    for (int i = 0; i < 8; i++) {
+        t += (int64_t)acc[i] - (int64_t)b[i];
+        acc[i] = (uint32_t)t;
+        t >>= 32;
+    }
+    bo = (uint32_t)(t & 1);
+#endif
+    return bo;
+}
+// acc[0..15] -= b[0..15] (mod 2^512)
+BN_HD void sub16(uint32_t* acc, const uint32_t* b) {
+    uint32_t bo = subi8b(acc, b, 0u);
+    (void)subi8b(acc + 8, b + 8, bo);
+}
+
 // 16-limb accumulate: acc[0..15] += b[0..15] (carry-out dropped: callers keep totals < 2^512).
 BN_HD void add16(uint32_t* acc, const uint32_t* b) {
     uint32_t c = addi8(acc, b);
@@ -506,6 +541,19 @@ BN_HD void wide_mac2(Wide& acc, const Fp& a, const Fp& b, const Fp& c, const Fp&
     add16(acc.w, E);
     add16_shift1(acc.w, O);
 }
+// T = a*b as a merged 512-bit integer (fresh E/O pair, then T = E + 2^32 O).  64 IMAD.WIDE.
+BN_HD void wide_mul(Wide& T, const Fp& a, const Fp& b) {
+    uint32_t E[18], O[16];
+    BN_UNROLL
+    for (int i = 0; i < 18; i++) E[i] = 0;
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) O[i] = 0;
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) eo_row(E, O, a.v, b.v[i], i);
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) T.w[i] = E[i];
+    add16_shift1(T.w, O);
+}
 // acc <<= 1 (value doubles; caller keeps it < 2^512)
 BN_HD void wide_dbl(Wide& acc) {
     BN_UNROLL
@@ -651,6 +699,11 @@ BN_HD Fp fp_mul(const Fp& a, const Fp& b) {
     Wide T = wide_zero();
     wide_mac1(T, a, b);
     return mont_reduce<M, 2>(T);
+}
+// out-of-line copy for the thread-per-element kernels (keeps their code inside the instruction cache)
+template <class M>
+BN_HD_NOINLINE Fp fp_mul_ni(const Fp& a, const Fp& b) {
+    return fp_mul<M>(a, b);
 }
 template <class M>
 BN_HD Fp fp_sqr(const Fp& a) {

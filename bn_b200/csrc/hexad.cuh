@@ -16,26 +16,48 @@
 // ring element.
 //
 // All functions are collective over the hexad: every lane calls them with its own coefficient.
-// `Ctx` supplies k() and shfl(value, source lane index within the hexad); kernels.cu binds it to
-// __shfl_sync, tests/host_emu binds it to a barrier exchange between six host threads.
+// `Ctx` supplies k(), shfl(value, source lane index within the hexad) and inv(Fq element, identical in the six
+// lanes); kernels.cu binds them to __shfl_sync and a block-wide batched inversion, tests/host_emu binds them to a
+// barrier exchange between six host threads and a plain Fermat inversion.
 #pragma once
 #include "fp2.cuh"
 
 namespace bn {
 
-// acc0 + acc1 i += x * y.  LAZY=false: y canonical (y1 negated as q - y1, each product < q^2);
-// LAZY=true: components of x, y < 2q (y1 negated as 2q - y1, each product < 4 q^2).
-template <bool LAZY>
-BN_HD void mac_fp2(AccEO& acc0, AccEO& acc1, const Fp2& x, const Fp2& y) {
-    Fp ny1 = LAZY ? fp_neg_2q(y.c1) : fp_neg_lazy<MQ>(y.c1);
-    acc_mac(acc0, x.c0, y.c0);
-    acc_mac(acc0, x.c1, ny1);
-    acc_mac(acc1, x.c0, y.c1);
-    acc_mac(acc1, x.c1, y.c0);
+// ------------------------------------------------------------------------------------------------
+// Lazy Fq2 multiply-accumulate on two merged 512-bit accumulators (arithmetic mod 2^512).
+//   a0 += x0 y0 - x1 y1          a1 += (x0+x1)(y0+y1) - x0 y0 - x1 y1        (Karatsuba: 3 x 64 IMAD.WIDE)
+// a0 starts at 6 q^2 (a multiple of q) so its true value never ends negative; a1's true value is
+// x0 y1 + x1 y0 >= 0, intermediate wrap-around is harmless.  Operands may be canonical or "lazy" (< 2q per
+// component, sums < 4q): every product stays < 16 q^2 < 2^512 and the final values stay < 12 q^2, which one
+// Montgomery reduction plus two conditional subtractions brings back to canonical form.
+// IMAD.WIDE is the scarce resource on B200 (quarter-rate), the ~170 IADD3 per step ride on the ALU pipe.
+// ------------------------------------------------------------------------------------------------
+struct AccK {
+    Wide a0, a1;
+};
+BN_HD void acck_init(AccK& A) {
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) {
+        A.a0.w[i] = WIDE_6Q2_f(i);
+        A.a1.w[i] = 0;
+    }
 }
-BN_HD Fp2 reduce2(const AccEO& acc0, const AccEO& acc1) {
-    return Fp2{mont_reduce<MQ, 4>(acc_merge(acc0)), mont_reduce<MQ, 4>(acc_merge(acc1))};
+BN_HD void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) {
+    Wide T;
+    wide_mul(T, x.c0, y.c0);
+    add16(A.a0.w, T.w);
+    sub16(A.a1.w, T.w);
+    wide_mul(T, x.c1, y.c1);
+    sub16(A.a0.w, T.w);
+    sub16(A.a1.w, T.w);
+    wide_mul(T, fp_add_raw(x.c0, x.c1), fp_add_raw(y.c0, y.c1));
+    add16(A.a1.w, T.w);
 }
+// one shared copy of the two Montgomery reductions (code footprint: the hot loop must stay inside the 32 KB I-cache)
+BN_HD_NOINLINE Fp2 reduce2(const AccK& A) { return Fp2{mont_reduce<MQ, 4>(A.a0), mont_reduce<MQ, 4>(A.a1)}; }
+BN_HD Fp2 fp2_mul_xi_shared(const Fp2& a) { return fp2_mul_xi(a); }  // fp2_mul_xi is itself out of line
+
 BN_HD int nib(uint32_t packed, int k) { return (int)((packed >> (4 * k)) & 7u); }
 BN_HD int mod6(int x) { return x >= 6 ? x - 6 : x; }
 
@@ -55,10 +77,9 @@ BN_HD Fp2 hx_conj(const Ctx& c, const Fp2& a) {
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul(const Ctx& c, const Fp2& a, const Fp2& b) {
     const int k = c.k();
-    Fp2 xa = fp2_mul_xi(a);
-    AccEO acc0, acc1;
-    acc_zero(acc0);
-    acc_zero(acc1);
+    Fp2 xa = fp2_mul_xi_shared(a);
+    AccK acc;
+    acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -67,45 +88,40 @@ BN_HD_NOINLINE Fp2 hx_mul(const Ctx& c, const Fp2& a, const Fp2& b) {
         Fp2 send = fp2_select(k + s >= 6, xa, a);
         Fp2 x = c.shfl(send, mod6(k + 6 - s));
         Fp2 y = c.shfl(b, s);
-        mac_fp2<false>(acc0, acc1, x, y);  // 6 steps * 2 q^2 per accumulator -> < 12 q^2
+        mac_fp2(acc, x, y);
     }
-    return reduce2(acc0, acc1);
+    return reduce2(acc);
 }
 
 // square.  reference src/fields/fq12.rs:275-282.  21 distinct products in 4 lock-step rounds:
-//   rounds 1-2: cross terms (the sender ships 2 a_i or 2 xi a_i)
-//   round 3   : even lanes a_i^2, odd lanes their third cross term
-//   round 4   : even lanes xi * a_j^2, odd lanes idle
+//   rounds 0-1: cross terms (the sender ships 2 a_i or 2 xi a_i)
+//   round 2   : even lanes a_i^2, odd lanes their third cross term
+//   round 3   : even lanes xi * a_j^2, odd lanes idle
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_sqr(const Ctx& c, const Fp2& a) {
     const int k = c.k();
-    Fp2 xa = fp2_mul_xi(a);
+    Fp2 xa = fp2_mul_xi_shared(a);
     Fp2 d = fp2_dbl(fp2_select(k >= 4, xa, a));  // doubled operand: 2 a_k on lanes 0..3, 2 xi a_k on lanes 4,5
-    AccEO acc0, acc1;
-    acc_zero(acc0);
-    acc_zero(acc1);
-    {   // round 1 (cross terms, sender pre-doubles): lane0: (2 xi a5) a1 ; lane k>0: (2 a0) a_k
-        Fp2 x = c.shfl(d, nib(0x000005u, k));
-        Fp2 y = c.shfl(a, nib(0x543211u, k));
-        mac_fp2<false>(acc0, acc1, x, y);
+    AccK acc;
+    acck_init(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = 0; r < 4; r++) {
+        // x sources / y sources per lane (nibble k), per round:
+        //  r0: (2xi a5) a1 | (2a0) a1 | (2a0) a2 | (2a0) a3 | (2a0) a4 | (2a0) a5
+        //  r1: (2xi a4) a2 | (2xi a5) a2 | (2xi a5) a3 | (2a1) a2 | (2a1) a3 | (2a1) a4
+        //  r2: a0 a0 | (2xi a4) a3 | a1 a1 | (2xi a4) a5 | a2 a2 | (2a3) a2
+        //  r3: xi a3 a3 | - | xi a4 a4 | - | xi a5 a5 | -
+        const uint32_t xs = r == 0 ? 0x000005u : r == 1 ? 0x111554u : r == 2 ? 0x324140u : 0x050403u;
+        const uint32_t ys = r == 0 ? 0x543211u : r == 1 ? 0x432322u : r == 2 ? 0x225130u : 0x050403u;
+        Fp2 send = fp2_select(r < 2 || (r == 2 && (k == 3 || k == 4)), d, fp2_select(r == 3, xa, a));
+        Fp2 x = c.shfl(send, nib(xs, k));
+        Fp2 y = c.shfl(a, nib(ys, k));
+        y = fp2_select(r == 3 && (k & 1) != 0, fp2_zero(), y);
+        mac_fp2(acc, x, y);
     }
-    {   // round 2: 2xi a4 a2 | 2xi a5 a2 | 2xi a5 a3 | 2 a1 a2 | 2 a1 a3 | 2 a1 a4
-        Fp2 x = c.shfl(d, nib(0x111554u, k));
-        Fp2 y = c.shfl(a, nib(0x432322u, k));
-        mac_fp2<false>(acc0, acc1, x, y);
-    }
-    {   // round 3: a0 a0 | (2 xi a4) a3 | a1 a1 | (2 xi a4) a5 | a2 a2 | (2 a3) a2
-        Fp2 x = c.shfl(fp2_select(k == 3 || k == 4, d, a), nib(0x324140u, k));
-        Fp2 y = c.shfl(a, nib(0x225130u, k));
-        mac_fp2<false>(acc0, acc1, x, y);
-    }
-    {   // round 4: xi a3 a3 | - | xi a4 a4 | - | xi a5 a5 | -
-        Fp2 x = c.shfl(xa, nib(0x050403u, k));
-        Fp2 y = c.shfl(a, nib(0x050403u, k));
-        y = fp2_select((k & 1) != 0, fp2_zero(), y);
-        mac_fp2<false>(acc0, acc1, x, y);
-    }
-    return reduce2(acc0, acc1);  // 4 rounds * 2 q^2 per accumulator
+    return reduce2(acc);
 }
 
 // product with the sparse line l0 + l3 w^3 + l4 w^4 (reference mul_by_024, src/fields/fq12.rs:107-176).
@@ -113,32 +129,36 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx& c, const Fp2& a) {
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx& c, const Fp2& a, const Fp2& l0, const Fp2& l3k, const Fp2& l4k) {
     const int k = c.k();
-    AccEO acc0, acc1;
-    acc_zero(acc0);
-    acc_zero(acc1);
-    mac_fp2<false>(acc0, acc1, a, l0);
-    Fp2 x3 = c.shfl(a, mod6(k + 3));  // a_{k-3}
-    mac_fp2<false>(acc0, acc1, x3, l3k);
-    Fp2 x4 = c.shfl(a, mod6(k + 2));  // a_{k-4}
-    mac_fp2<false>(acc0, acc1, x4, l4k);
-    return reduce2(acc0, acc1);
+    AccK acc;
+    acck_init(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = 0; r < 3; r++) {
+        Fp2 x = c.shfl(a, mod6(k + (r == 0 ? 0 : r == 1 ? 3 : 2)));  // a_k, a_{k-3}, a_{k-4}
+        Fp2 y = fp2_select(r == 0, l0, fp2_select(r == 1, l3k, l4k));
+        mac_fp2(acc, x, y);
+    }
+    return reduce2(acc);
 }
 
 // product with an Fq6 element m0 + m1 v + m2 v^2 = m0 + m1 w^2 + m2 w^4 known to every lane.
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx& c, const Fp2& a, const Fp2& m0, const Fp2& m1, const Fp2& m2) {
     const int k = c.k();
-    Fp2 m1k = fp2_select(k < 2, fp2_mul_xi(m1), m1);
-    Fp2 m2k = fp2_select(k < 4, fp2_mul_xi(m2), m2);
-    AccEO acc0, acc1;
-    acc_zero(acc0);
-    acc_zero(acc1);
-    mac_fp2<false>(acc0, acc1, a, m0);
-    Fp2 x2 = c.shfl(a, mod6(k + 4));  // a_{k-2}
-    mac_fp2<false>(acc0, acc1, x2, m1k);
-    Fp2 x4 = c.shfl(a, mod6(k + 2));  // a_{k-4}
-    mac_fp2<false>(acc0, acc1, x4, m2k);
-    return reduce2(acc0, acc1);
+    Fp2 m1k = fp2_select(k < 2, fp2_mul_xi_shared(m1), m1);
+    Fp2 m2k = fp2_select(k < 4, fp2_mul_xi_shared(m2), m2);
+    AccK acc;
+    acck_init(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = 0; r < 3; r++) {
+        Fp2 x = c.shfl(a, mod6(k + (r == 0 ? 0 : r == 1 ? 4 : 2)));  // a_k, a_{k-2}, a_{k-4}
+        Fp2 y = fp2_select(r == 0, m0, fp2_select(r == 1, m1k, m2k));
+        mac_fp2(acc, x, y);
+    }
+    return reduce2(acc);
 }
 
 // Frobenius x -> x^(q^p), p in {1,2,3}: conj^p on each coefficient, times xi^(k (q^p-1)/6).
@@ -159,7 +179,7 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx& c, const Fp2& a) {
     const bool pre = (k & 1) == 0;  // lanes 0,2,4 form (x+y)(x+xi y); lanes 3,5,1 form x*y
     // pair assignment: lane0,3 <- (g0,g3); lane2,5 <- (g1,g4); lane4,1 <- (g2,g5)
     const int lo = nib(0x120120u, k), hi = lo + 3;
-    Fp2 xa = fp2_mul_xi(a);
+    Fp2 xa = fp2_mul_xi_shared(a);
     Fp2 x = c.shfl(a, lo);
     Fp2 y = c.shfl(a, hi);
     Fp2 xy = c.shfl(xa, hi);
@@ -168,16 +188,15 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx& c, const Fp2& a) {
     f0.c1 = fp_add_raw(x.c1, fp_select(pre, y.c1, fp_zero()));
     f1.c0 = fp_add_raw(fp_select(pre, xy.c0, y.c0), fp_select(pre, x.c0, fp_zero()));
     f1.c1 = fp_add_raw(fp_select(pre, xy.c1, y.c1), fp_select(pre, x.c1, fp_zero()));
-    AccEO acc0, acc1;
-    acc_zero(acc0);
-    acc_zero(acc1);
-    mac_fp2<true>(acc0, acc1, f0, f1);  // < 8 q^2
-    Fp2 r = reduce2(acc0, acc1);
+    AccK acc;
+    acck_init(acc);
+    mac_fp2(acc, f0, f1);
+    Fp2 r = reduce2(acc);
     // partner product: lane0 <- lane3, lane2 <- lane5, lane4 <- lane1
     Fp2 tmp = c.shfl(r, nib(0x010503u, k));
     Fp2 r2 = fp2_add(r, r);
     // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*t5 on lane 1
-    Fp2 xo = fp2_mul_xi(fp2_select(pre, tmp, r2));
+    Fp2 xo = fp2_mul_xi_shared(fp2_select(pre, tmp, r2));
     Fp2 t_pre = fp2_sub(fp2_sub(r, tmp), xo);               // t0 / t2 / t4
     Fp2 t_im = fp2_select(k == 1, xo, r2);                   // t1 / t3 / xi*t5
     Fp2 t = fp2_select(pre, t_pre, t_im);
@@ -211,7 +230,12 @@ BN_HD_NOINLINE Fp2 hx_inv(const Ctx& c, const Fp2& f) {
     Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(n2)), fp2_mul(n0, n1));
     Fp2 t2 = fp2_sub(fp2_sqr(n1), fp2_mul(n0, n2));
     Fp2 dd = fp2_add(fp2_mul_xi(fp2_add(fp2_mul(n2, t1), fp2_mul(n1, t2))), fp2_mul(n0, t0));
-    Fp2 di = fp2_inv(dd);
+    // 1/dd = conj(dd) / (d0^2 + d1^2); the Fq inversion is delegated to the context so a kernel can batch it
+    // (Montgomery's trick over all hexads of a thread block: one Fermat chain per block instead of one per warp)
+    Wide nn = wide_zero();
+    wide_mac2(nn, dd.c0, dd.c0, dd.c1, dd.c1);
+    Fp ninv = c.inv(mont_reduce<MQ, 2>(nn));
+    Fp2 di = Fp2{fp_mul<MQ>(dd.c0, ninv), fp_neg<MQ>(fp_mul<MQ>(dd.c1, ninv))};
     return hx_mul_fq6(c, fc, fp2_mul(di, t0), fp2_mul(di, t1), fp2_mul(di, t2));
 }
 

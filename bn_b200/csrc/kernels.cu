@@ -44,8 +44,22 @@ __device__ __forceinline__ void st_fp2(uint32_t* p, const Fp2& a) {
     st_fp(p + 8, a.c1);
 }
 
+#ifndef HEX_WARPS_PER_BLOCK
+#define HEX_WARPS_PER_BLOCK 4
+#endif
+#define HEX_PER_WARP 5
+#define HEX_PER_BLOCK (HEX_WARPS_PER_BLOCK * HEX_PER_WARP)
+
+// Shared scratch of a hexad block: one Fq slot per hexad + prefix products for the batched inversion.
+struct HexSmem {
+    Fp val[HEX_PER_BLOCK];
+    Fp pre[HEX_PER_BLOCK];
+};
+
 struct DevCtx {
     int kk, base;
+    int slot;        // hexad index inside the block, or -1 for the two spare lanes of a warp
+    HexSmem* sm;
     __device__ __forceinline__ int k() const { return kk; }
     __device__ __forceinline__ Fp2 shfl(const Fp2& v, int src) const {
         Fp2 r;
@@ -56,6 +70,31 @@ struct DevCtx {
             r.c1.v[i] = __shfl_sync(0xffffffffu, v.c1.v[i], lane);
         }
         return r;
+    }
+    // 1/x for the x of every hexad in the block with ONE Fermat chain (Montgomery's simultaneous inversion):
+    // prefix products, invert the total, peel back.  Collective over the whole block (two __syncthreads).
+    // A zero input (only possible for garbage lanes / infinity pairs, whose result is discarded) is replaced by 1
+    // so it cannot poison the other pairings' product.
+    __device__ __noinline__ Fp inv(const Fp& x) const {
+        if (kk == 0 && slot >= 0) sm->val[slot] = fp_is_zero(x) ? fq_one() : x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Fp acc = sm->val[0];
+            sm->pre[0] = acc;
+            for (int i = 1; i < HEX_PER_BLOCK; i++) {
+                acc = fp_mul<MQ>(acc, sm->val[i]);
+                sm->pre[i] = acc;
+            }
+            Fp t = fp_inv<MQ>(acc);
+            for (int i = HEX_PER_BLOCK - 1; i > 0; i--) {
+                Fp vi = sm->val[i];
+                sm->val[i] = fp_mul<MQ>(t, sm->pre[i - 1]);
+                t = fp_mul<MQ>(t, vi);
+            }
+            sm->val[0] = t;
+        }
+        __syncthreads();
+        return sm->val[slot >= 0 ? slot : 0];
     }
 };
 
@@ -99,21 +138,30 @@ __global__ void __launch_bounds__(256) k_fq_mul_chain(const uint32_t* __restrict
 // Calibration: nothing but independent IMAD.WIDE.U32 chains (8 accumulator pairs per thread), to measure the
 // fma-pipe integer-multiply issue rate the pairing kernels are bounded by.  32 IMAD.WIDE per loop trip.
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* __restrict__ out, uint32_t iters, uint32_t seed) {
-    uint64_t acc[8];
-    const uint32_t y = blockIdx.x * 40503u + 12345u + seed;
+    // four independent accumulator windows, each fed by 4-IMAD carry chains (the exact instruction the field
+    // arithmetic is made of: IMAD.WIDE.U32.X); 32 IMAD.WIDE per loop trip, no other arithmetic.
+    uint32_t acc[4][8];
+    uint32_t x[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = ((uint64_t)(threadIdx.x * 2654435761u + j) << 7) | 1u;
+    for (int j = 0; j < 4; j++) {
+        x[j] = threadIdx.x * 2654435761u + seed + j;
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[j][i] = blockIdx.x + i * 7 + j;
+    }
+    uint32_t y = blockIdx.x * 40503u + 12345u;
     for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < 2; r++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[j] = (uint64_t)(uint32_t)acc[j] * y + acc[j];  // IMAD.WIDE.U32 Rd, Rd.lo, y, Rd
+            for (int j = 0; j < 4; j++) mad_row4_nc(acc[j], x[0], x[1], x[2], x[3], y + j);
         }
     }
-    uint64_t s = 0;
+    uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) s ^= acc[j];
-    if (s == 0x123456789abcdefULL) out[0] = (uint32_t)s;  // practically never: keeps the chains live
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) s ^= acc[j][i];
+    if (s == 0x12345678u && y == 3) out[0] = s;  // practically never: keeps the chains live
 }
 
 __global__ void __launch_bounds__(128) k_g1_mul(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k,
@@ -220,10 +268,6 @@ __global__ void __launch_bounds__(64) k_pair_lines_duo(const uint32_t* __restric
     ate_lines(X_, px, py, qx, qy, sink);
 }
 
-#ifndef HEX_WARPS_PER_BLOCK
-#define HEX_WARPS_PER_BLOCK 4
-#endif
-#define HEX_PER_WARP 5
 #ifndef HEX_MIN_BLOCKS
 #define HEX_MIN_BLOCKS 1   // blocks/SM promised to ptxas for the hexad kernels (register cap = 65536 / (threads * blocks))
 #endif
@@ -233,13 +277,15 @@ struct HexIndex {
     size_t pidx;   // pairing / element index (clamped to a valid one)
     bool active;   // this lane belongs to a real element
 };
-__device__ __forceinline__ HexIndex hex_index(size_t n) {
+__device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int hex = lane / 6;  // 0..5 (5 = the two spare lanes)
     HexIndex h;
     h.ctx.kk = lane - hex * 6;
     h.ctx.base = hex * 6;
+    h.ctx.slot = hex < HEX_PER_WARP ? warp * HEX_PER_WARP + hex : -1;
+    h.ctx.sm = sm;
     size_t idx = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP + hex;
     h.active = (hex < HEX_PER_WARP) && (idx < n);
     h.pidx = h.active ? idx : (n - 1);
@@ -249,7 +295,8 @@ __device__ __forceinline__ HexIndex hex_index(size_t n) {
 // K4b: Miller loop + final exponentiation, one hexad per pairing.
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
 k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
-    HexIndex h = hex_index(n);
+    __shared__ HexSmem smem;
+    HexIndex h = hex_index(n, &smem);
     DevLineSrc src{lines, n, h.pidx};
     Fp2 f = hx_miller_loop(h.ctx, src);
     f = hx_final_exp(h.ctx, f);
@@ -259,7 +306,8 @@ k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ fl
 
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
 k_gt_mul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n) {
-    HexIndex h = hex_index(n);
+    __shared__ HexSmem smem;
+    HexIndex h = hex_index(n, &smem);
     const int slot = 16 * gt_slot(h.ctx.kk);
     Fp2 x = ld_fp2(a + h.pidx * 96 + slot), y = ld_fp2(b + h.pidx * 96 + slot);
     Fp2 r = hx_mul(h.ctx, x, y);
@@ -268,7 +316,8 @@ k_gt_mul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_
 
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
 k_gt_pow(const uint32_t* __restrict__ a, const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
-    HexIndex h = hex_index(n);
+    __shared__ HexSmem smem;
+    HexIndex h = hex_index(n, &smem);
     const int slot = 16 * gt_slot(h.ctx.kk);
     Fp2 x = ld_fp2(a + h.pidx * 96 + slot);
     Fp e = fp_from_mont<ModR>(ld_fp(k + h.pidx * 8));  // U256::from(Fr), reference src/fields/fp.rs:15-22

@@ -58,6 +58,7 @@ struct HostCtx {
     int kk;
     HostHexShared* sh;
     int k() const { return kk; }
+    Fp inv(const Fp& x) const { return fp_inv<ModQ>(x); }
     Fp2 shfl(const Fp2& v, int src) const {
         sh->slot[kk] = v;
         sh->bar.wait();
