@@ -210,14 +210,16 @@ BN_HD void g2_mul_by_q(const X& X_, Fp2& x, Fp2& y) {
 // Affine coordinates of a (G1, G2) pair with ONE field inversion for both points
 // (reference to_affine, src/groups/mod.rs:113-130, inverts P.z and Q.z separately; the values are the same).
 // Returns false when either point is the point at infinity (pairing = one, src/groups/mod.rs:765-766).
-template <class X>
-BN_HD bool pair_to_affine(const X& X_, const Jac<FqOps>& P, const Jac<Fq2Ops>& Q, Fp& px, Fp& py, Fp2& qx, Fp2& qy) {
+// `inv` is a callable Fp -> Fp (plain Fermat inversion, or a block-wide batched inversion in the kernels).
+template <class X, class Inv>
+BN_HD bool pair_to_affine(const X& X_, const Inv& inv, const Jac<FqOps>& P, const Jac<Fq2Ops>& Q, Fp& px, Fp& py, Fp2& qx,
+                          Fp2& qy) {
     bool inf = fp_is_zero(P.z) || fp2_is_zero(Q.z);
     Wide n = wide_zero();
     wide_mac2(n, Q.z.c0, Q.z.c0, Q.z.c1, Q.z.c1);
     Fp nq = mont_reduce<MQ, 2>(n);         // |Q.z|^2 in Fq
     Fp t = fp_mul<MQ>(P.z, nq);
-    Fp tinv = fp_inv<MQ>(fp_select(inf, fq_one(), t));
+    Fp tinv = inv(fp_select(inf, fq_one(), t));
     Fp pzinv = fp_mul<MQ>(tinv, nq);
     Fp nqinv = fp_mul<MQ>(tinv, P.z);
     Fp2 qzinv = Fp2{fp_mul<MQ>(Q.z.c0, nqinv), fp_neg<MQ>(fp_mul<MQ>(Q.z.c1, nqinv))};
@@ -229,6 +231,10 @@ BN_HD bool pair_to_affine(const X& X_, const Jac<FqOps>& P, const Jac<Fq2Ops>& Q
     qy = X_.mul(Q.y, X_.mul(qz2, qzinv));
     return !inf;
 }
+
+struct FermatInv {
+    BN_HD Fp operator()(const Fp& x) const { return fp_inv<MQ>(x); }
+};
 
 // Emit the 102 lines for affine (P, Q) in Miller-loop order.  sink(index, line).
 // reference precompute, src/groups/mod.rs:557-588

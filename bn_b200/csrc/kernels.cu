@@ -49,12 +49,43 @@ __device__ __forceinline__ void st_fp2(uint32_t* p, const Fp2& a) {
 #endif
 #define HEX_PER_WARP 5
 #define HEX_PER_BLOCK (HEX_WARPS_PER_BLOCK * HEX_PER_WARP)
+#ifndef HEX_BATCH_INV
+#define HEX_BATCH_INV 1   // final-exponentiation Fq inversion: one Fermat chain per block (1) or per lane (0)
+#endif
 
 // Shared scratch of a hexad block: one Fq slot per hexad + prefix products for the batched inversion.
 struct HexSmem {
     Fp val[HEX_PER_BLOCK];
     Fp pre[HEX_PER_BLOCK];
 };
+
+// 1/x for one x per "slot" of a thread block with ONE Fermat chain (Montgomery's simultaneous inversion):
+// prefix products, invert the total, peel back.  Collective over the whole block (two __syncthreads); the chain
+// runs on one thread while the other warps of the block yield their issue slots to the SM's other blocks.
+// wslot: slot this thread writes (-1: none); rslot: slot it reads back (-1: slot 0, value unused).
+// A zero input (only possible for infinity pairs / padding lanes, whose result is discarded) is replaced by 1 so it
+// cannot poison the other elements' product.
+__device__ __noinline__ Fp block_batch_inv(const Fp& x, int wslot, int rslot, int nslots, Fp* val, Fp* pre) {
+    if (wslot >= 0) val[wslot] = fp_is_zero(x) ? fq_one() : x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Fp acc = val[0];
+        pre[0] = acc;
+        for (int i = 1; i < nslots; i++) {
+            acc = fp_mul<MQ>(acc, val[i]);
+            pre[i] = acc;
+        }
+        Fp t = fp_inv<MQ>(acc);
+        for (int i = nslots - 1; i > 0; i--) {
+            Fp vi = val[i];
+            val[i] = fp_mul<MQ>(t, pre[i - 1]);
+            t = fp_mul<MQ>(t, vi);
+        }
+        val[0] = t;
+    }
+    __syncthreads();
+    return val[rslot >= 0 ? rslot : 0];
+}
 
 struct DevCtx {
     int kk, base;
@@ -75,26 +106,12 @@ struct DevCtx {
     // prefix products, invert the total, peel back.  Collective over the whole block (two __syncthreads).
     // A zero input (only possible for garbage lanes / infinity pairs, whose result is discarded) is replaced by 1
     // so it cannot poison the other pairings' product.
-    __device__ __noinline__ Fp inv(const Fp& x) const {
-        if (kk == 0 && slot >= 0) sm->val[slot] = fp_is_zero(x) ? fq_one() : x;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            Fp acc = sm->val[0];
-            sm->pre[0] = acc;
-            for (int i = 1; i < HEX_PER_BLOCK; i++) {
-                acc = fp_mul<MQ>(acc, sm->val[i]);
-                sm->pre[i] = acc;
-            }
-            Fp t = fp_inv<MQ>(acc);
-            for (int i = HEX_PER_BLOCK - 1; i > 0; i--) {
-                Fp vi = sm->val[i];
-                sm->val[i] = fp_mul<MQ>(t, sm->pre[i - 1]);
-                t = fp_mul<MQ>(t, vi);
-            }
-            sm->val[0] = t;
-        }
-        __syncthreads();
-        return sm->val[slot >= 0 ? slot : 0];
+    __device__ __forceinline__ Fp inv(const Fp& x) const {
+#if HEX_BATCH_INV
+        return block_batch_inv(x, kk == 0 ? slot : -1, slot, HEX_PER_BLOCK, sm->val, sm->pre);
+#else
+        return fp_inv<MQ>(x);
+#endif
     }
 };
 
@@ -208,7 +225,7 @@ __global__ void __launch_bounds__(64) k_pair_lines(const uint32_t* __restrict__ 
     Fp px, py;
     Fp2 qx, qy;
     SoloX X_;
-    bool finite = pair_to_affine(X_, P, Q, px, py, qx, qy);
+    bool finite = pair_to_affine(X_, FermatInv(), P, Q, px, py, qx, qy);
     flags[i] = finite ? 1 : 0;
     DevLineSink sink{lines, n, i};
     ate_lines(X_, px, py, qx, qy, sink);
@@ -262,7 +279,10 @@ __global__ void __launch_bounds__(64) k_pair_lines_duo(const uint32_t* __restric
     DuoX<DevDuo> X_{DevDuo{(int)(t & 1)}};
     Fp px, py;
     Fp2 qx, qy;
-    bool finite = pair_to_affine(X_, P, Q, px, py, qx, qy);
+    __shared__ Fp s_val[32], s_pre[32];  // 64 threads = 32 pairings per block
+    const int slot = (int)(threadIdx.x >> 1);
+    auto inv = [&](const Fp& x) { return block_batch_inv(x, (threadIdx.x & 1) == 0 ? slot : -1, slot, 32, s_val, s_pre); };
+    bool finite = pair_to_affine(X_, inv, P, Q, px, py, qx, qy);
     if (active && (t & 1) == 0) flags[i] = finite ? 1 : 0;
     DevDuoLineSink sink{lines, n, i, (int)(t & 1), active};
     ate_lines(X_, px, py, qx, qy, sink);

@@ -12,10 +12,17 @@ namespace bn {
 //   l3k = (k < 3 ? xi*l3 : l3),  l4k = (k < 4 ? xi*l4 : l4)
 template <class Ctx, class LineSrc>
 BN_HD Fp2 hx_miller_loop(const Ctx& c, const LineSrc& src) {
-    Fp2 f = hx_one(c);
     Fp2 l0, l3k, l4k;
     int t = 0;
-    for (int b = BN_ATE_NBITS - 1; b >= 0; b--) {
+    // first iteration: f = 1, so f^2 * line is the line itself: l0 + l3 w^3 + l4 w^4 (lanes 3 and 4 hold the
+    // plain l3 / l4 variants, see LineSrc::get)
+    src.get(t++, c.k(), l0, l3k, l4k);
+    Fp2 f = fp2_select(c.k() == 0, l0, fp2_select(c.k() == 3, l3k, fp2_select(c.k() == 4, l4k, fp2_zero())));
+    if ((BN_ATE_BITS >> (BN_ATE_NBITS - 1)) & 1ULL) {
+        src.get(t++, c.k(), l0, l3k, l4k);
+        f = hx_mul_line(c, f, l0, l3k, l4k);
+    }
+    for (int b = BN_ATE_NBITS - 2; b >= 0; b--) {
         f = hx_sqr(c, f);
         src.get(t++, c.k(), l0, l3k, l4k);
         f = hx_mul_line(c, f, l0, l3k, l4k);

@@ -174,7 +174,7 @@ void emu_g2_mul(const uint64_t* p, const uint64_t* fr, uint64_t* out) {
 int emu_lines(const uint64_t* g1, const uint64_t* g2, uint64_t* lines, uint64_t* p_affine8, uint64_t* q_affine16) {
     Fp px, py; Fp2 qx, qy;
     SoloX X_;
-    bool ok = pair_to_affine(X_, load_g1(g1), load_g2(g2), px, py, qx, qy);
+    bool ok = pair_to_affine(X_, FermatInv(), load_g1(g1), load_g2(g2), px, py, qx, qy);
     if (p_affine8) { store_fp(p_affine8, px); store_fp(p_affine8 + 4, py); }
     if (q_affine16) { store_fp2(q_affine16, qx); store_fp2(q_affine16 + 8, qy); }
     HostLineSink sink{lines};
@@ -191,7 +191,7 @@ int emu_lines_duo(const uint64_t* g1, const uint64_t* g2, uint64_t* lines_lane0,
         th.emplace_back([&, h]() {
             DuoX<HostDuo> X_{HostDuo{h, &sh}};
             Fp px, py; Fp2 qx, qy;
-            ok[h] = pair_to_affine(X_, load_g1(g1), load_g2(g2), px, py, qx, qy) ? 1 : 0;
+            ok[h] = pair_to_affine(X_, FermatInv(), load_g1(g1), load_g2(g2), px, py, qx, qy) ? 1 : 0;
             HostLineSink sink{outs[h]};
             ate_lines(X_, px, py, qx, qy, sink);
         });
