@@ -33,6 +33,37 @@ namespace bn {
 // Montgomery reduction plus two conditional subtractions brings back to canonical form.
 // IMAD.WIDE is the scarce resource on B200 (quarter-rate), the ~170 IADD3 per step ride on the ALU pipe.
 // ------------------------------------------------------------------------------------------------
+#ifndef BN_ACC3
+#define BN_ACC3 0
+#endif
+#if BN_ACC3
+// Variant: three carry-save accumulators (P0 = sum x0 y0, P1 = sum x1 y1, P2 = sum (x0+x1)(y0+y1)); the round loop is
+// then almost pure IMAD.WIDE (one IADD3.X per 4-IMAD chain) and the Karatsuba recombination happens once per
+// reduction.  Costs 120 accumulator registers.
+struct AccK {
+    AccEO p0, p1, p2;
+};
+BN_HD void acck_init(AccK& A) {
+    acc_zero(A.p0);
+    acc_zero(A.p1);
+    acc_zero(A.p2);
+}
+BN_HD void mac_fp2_inl(AccK& A, const Fp2& x, const Fp2& y) {
+    acc_mac(A.p0, x.c0, y.c0);
+    acc_mac(A.p1, x.c1, y.c1);
+    acc_mac(A.p2, fp_add_raw(x.c0, x.c1), fp_add_raw(y.c0, y.c1));
+}
+BN_HD void acck_finish(const AccK& A, Wide& a0, Wide& a1) {
+    Wide t0 = acc_merge(A.p0), t1 = acc_merge(A.p1);
+    a1 = acc_merge(A.p2);
+    sub16(a1.w, t0.w);
+    sub16(a1.w, t1.w);
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) a0.w[i] = WIDE_6Q2_f(i);
+    add16(a0.w, t0.w);
+    sub16(a0.w, t1.w);
+}
+#else
 struct AccK {
     Wide a0, a1;
 };
@@ -43,7 +74,7 @@ BN_HD void acck_init(AccK& A) {
         A.a1.w[i] = 0;
     }
 }
-BN_HD void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) {
+BN_HD void mac_fp2_inl(AccK& A, const Fp2& x, const Fp2& y) {
     Wide T;
     wide_mul(T, x.c0, y.c0);
     add16(A.a0.w, T.w);
@@ -54,8 +85,27 @@ BN_HD void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) {
     wide_mul(T, fp_add_raw(x.c0, x.c1), fp_add_raw(y.c0, y.c1));
     add16(A.a1.w, T.w);
 }
+BN_HD void acck_finish(const AccK& A, Wide& a0, Wide& a1) {
+    a0 = A.a0;
+    a1 = A.a1;
+}
+#endif
 // one shared copy of the two Montgomery reductions (code footprint: the hot loop must stay inside the 32 KB I-cache)
-BN_HD_NOINLINE Fp2 reduce2(const AccK& A) { return Fp2{mont_reduce<MQ, 4>(A.a0), mont_reduce<MQ, 4>(A.a1)}; }
+#ifndef BN_MAC_NOINLINE
+#define BN_MAC_NOINLINE 0
+#endif
+#if BN_MAC_NOINLINE
+// one shared out-of-line copy of the multiply-accumulate (operands and accumulators travel through local memory)
+BN_HD_NOINLINE void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) { mac_fp2_inl(A, x, y); }
+#else
+BN_HD void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) { mac_fp2_inl(A, x, y); }
+#endif
+BN_HD_NOINLINE Fp2 reduce2_wide(const Wide& a0, const Wide& a1) { return Fp2{mont_reduce<MQ, 4>(a0), mont_reduce<MQ, 4>(a1)}; }
+BN_HD Fp2 reduce2(const AccK& A) {
+    Wide a0, a1;
+    acck_finish(A, a0, a1);
+    return reduce2_wide(a0, a1);
+}
 BN_HD Fp2 fp2_mul_xi_shared(const Fp2& a) { return fp2_mul_xi(a); }  // fp2_mul_xi is itself out of line
 
 BN_HD int nib(uint32_t packed, int k) { return (int)((packed >> (4 * k)) & 7u); }

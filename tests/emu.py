@@ -17,7 +17,7 @@ def lib():
         csrc = os.path.join(os.path.dirname(_HERE), "..", "bn_b200", "csrc")
         deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".inc"))]
         if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", _SO, src, "-lpthread"])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", *os.environ.get("BN_EMU_FLAGS", "").split(), "-shared", "-fPIC", "-o", _SO, src, "-lpthread"])
         _lib = ctypes.CDLL(_SO)
     return _lib
 
