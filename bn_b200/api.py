@@ -62,6 +62,15 @@ def gt_mul_batch(a, b, device: int = 0) -> np.ndarray:
     return _binary("bn_b200_gt_mul_batch", a, GT_WORDS, b, GT_WORDS, GT_WORDS, device)
 
 
+def gt_inv_batch(a, device: int = 0) -> np.ndarray:
+    """a[i].inverse().  reference Gt::inverse, src/lib.rs:172."""
+    lib = _lib.init(device)
+    a = _arr(a, GT_WORDS)
+    out = np.empty_like(a)
+    _lib.check(lib.bn_b200_gt_inv_batch(_p(a), _p(out), ctypes.c_size_t(len(a))))
+    return out
+
+
 def fq_mul_chain(a, b, iters: int, device: int = 0) -> np.ndarray:
     """x <- x*b (Montgomery mod q) `iters` times per element (BASELINE config 2)."""
     lib = _lib.init(device)
@@ -115,6 +124,9 @@ class Gt(_Img):
 
     def __mul__(self, other: "Gt") -> "Gt":
         return Gt(gt_mul_batch(self.img[None], other.img[None])[0])
+
+    def inverse(self) -> "Gt":
+        return Gt(gt_inv_batch(self.img[None])[0])
 
 
 def pairing(p: G1, q: G2) -> Gt:

@@ -20,7 +20,7 @@ BN_HD Fp2 duo_join(const D& d, const Fp& mine) {
 
 // reference src/fields/fq2.rs:139-155
 template <class D>
-BN_HD_NOINLINE Fp2 duo_mul(const D& d, const Fp2& a, const Fp2& b) {
+BN_HD_NOINLINE Fp2 duo_mul(const D d, Fp2 a, Fp2 b) {
     const bool h = d.h() != 0;
     // lane 0: a0*b0 + a1*(q - b1) ; lane 1: a0*b1 + a1*b0
     Fp y0 = fp_select(h, b.c1, b.c0);
@@ -31,7 +31,7 @@ BN_HD_NOINLINE Fp2 duo_mul(const D& d, const Fp2& a, const Fp2& b) {
 }
 // reference src/fields/fq2.rs:112-123
 template <class D>
-BN_HD_NOINLINE Fp2 duo_sqr(const D& d, const Fp2& a) {
+BN_HD_NOINLINE Fp2 duo_sqr(const D d, Fp2 a) {
     const bool h = d.h() != 0;
     // lane 0: (a0 + a1)(a0 + (q - a1)) ; lane 1: 2 * a0*a1
     Fp x = fp_select(h, a.c0, fp_add_raw(a.c0, a.c1));
@@ -46,12 +46,12 @@ BN_HD_NOINLINE Fp2 duo_sqr(const D& d, const Fp2& a) {
 }
 // reference src/fields/fq2.rs:63-68
 template <class D>
-BN_HD_NOINLINE Fp2 duo_mul_fp(const D& d, const Fp2& a, const Fp& k) {
+BN_HD_NOINLINE Fp2 duo_mul_fp(const D d, Fp2 a, Fp k) {
     return duo_join(d, fp_mul<MQ>(d.h() ? a.c1 : a.c0, k));
 }
 // xi * a, one component per lane: lane 0: 9 a0 - a1, lane 1: 9 a1 + a0.   reference src/fields/fq2.rs:70-72
 template <class D>
-BN_HD_NOINLINE Fp2 duo_mul_xi(const D& d, const Fp2& a) {
+BN_HD_NOINLINE Fp2 duo_mul_xi(const D d, Fp2 a) {
     const bool h = d.h() != 0;
     Fp x = fp_select(h, a.c1, a.c0);
     Fp addend = fp_select(h, a.c0, fp_neg_lazy<MQ>(a.c1));

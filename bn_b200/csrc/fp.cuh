@@ -358,7 +358,7 @@ BN_HD void add16_shift1(uint32_t* acc, const uint32_t* b) {
 // ------------------------------------------------------------------------------------------------
 // Field element + modulus descriptors
 // ------------------------------------------------------------------------------------------------
-struct Fp {
+struct alignas(16) Fp {
     uint32_t v[8];
 };
 
@@ -493,7 +493,7 @@ BN_HD Fp fp_half(const Fp& a) {
 // ------------------------------------------------------------------------------------------------
 // 512-bit products in (E, O) form and their accumulation
 // ------------------------------------------------------------------------------------------------
-struct Wide {
+struct alignas(16) Wide {
     uint32_t w[16];
 };
 BN_HD Wide wide_zero() {
@@ -702,7 +702,7 @@ BN_HD Fp fp_mul(const Fp& a, const Fp& b) {
 }
 // out-of-line copy for the thread-per-element kernels (keeps their code inside the instruction cache)
 template <class M>
-BN_HD_NOINLINE Fp fp_mul_ni(const Fp& a, const Fp& b) {
+BN_HD_NOINLINE Fp fp_mul_ni(Fp a, Fp b) {
     return fp_mul<M>(a, b);
 }
 template <class M>
@@ -721,7 +721,7 @@ BN_HD Fp fp_from_mont(const Fp& a) {
 // x^(p-2): same canonical value as reference Fq::inverse (src/fields/fp.rs:103-112; binary Euclid there,
 // Fermat here -- the inverse is unique, so the Montgomery limbs agree).  x must be non-zero.
 template <class M>
-BN_HD_NOINLINE Fp fp_inv(const Fp& x) {
+BN_HD_NOINLINE Fp fp_inv(Fp x) {
     // exponent p-2, MSB first; p-2 has bit 253 set.
     Fp r = x;
     for (int bit = 252; bit >= 0; bit--) {

@@ -68,7 +68,7 @@ BN_HD Fp fp_neg_2q(const Fp& a) {
 
 // (a0 + a1 i)(b0 + b1 i), schoolbook on 512-bit accumulators: 4 products, 2 reductions.
 // reference src/fields/fq2.rs:139-155 (Karatsuba + 3-4 reductions there; same canonical result).
-BN_HD_NOINLINE Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+BN_HD_NOINLINE Fp2 fp2_mul(Fp2 a, Fp2 b) {
     Fp nb1 = fp_neg_lazy<MQ>(b.c1);
     Wide t0 = wide_zero(), t1 = wide_zero();
     wide_mac2(t0, a.c0, b.c0, a.c1, nb1);   // a0 b0 - a1 b1   (< 2 q^2)
@@ -76,7 +76,7 @@ BN_HD_NOINLINE Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
     return Fp2{mont_reduce<MQ, 2>(t0), mont_reduce<MQ, 2>(t1)};
 }
 // (a0+a1)(a0-a1) + 2 a0 a1 i.   reference src/fields/fq2.rs:112-123
-BN_HD_NOINLINE Fp2 fp2_sqr(const Fp2& a) {
+BN_HD_NOINLINE Fp2 fp2_sqr(Fp2 a) {
     Fp s = fp_add_raw(a.c0, a.c1);                      // < 2q
     Fp d = fp_add_raw(a.c0, fp_neg_lazy<MQ>(a.c1));     // a0 + (q - a1) in (0, 2q)
     Wide t0 = wide_zero(), t1 = wide_zero();
@@ -111,7 +111,7 @@ BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out) {
 }
 
 // multiply by xi = 9 + i:  (9x - y) + (9y + x) i.   reference src/fields/fq2.rs:70-72 (a full Fq2 mul there)
-BN_HD_NOINLINE Fp2 fp2_mul_xi(const Fp2& a) {
+BN_HD_NOINLINE Fp2 fp2_mul_xi(Fp2 a) {
     Fp2 r;
     // component 0: 9*a0 + (q - a1)  in (0, 10q];  component 1: 9*a1 + a0 in [0, 10q)
     BN_UNROLL

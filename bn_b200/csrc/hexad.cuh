@@ -95,12 +95,16 @@ BN_HD void acck_finish(const AccK& A, Wide& a0, Wide& a1) {
 #define BN_MAC_NOINLINE 0
 #endif
 #if BN_MAC_NOINLINE
-// one shared out-of-line copy of the multiply-accumulate (operands and accumulators travel through local memory)
-BN_HD_NOINLINE void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) { mac_fp2_inl(A, x, y); }
+// one shared out-of-line copy of the multiply-accumulate
+BN_HD_NOINLINE AccK mac_fp2_call(AccK A, Fp2 x, Fp2 y) {  // by value: everything travels in registers
+    mac_fp2_inl(A, x, y);
+    return A;
+}
+BN_HD void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) { A = mac_fp2_call(A, x, y); }
 #else
 BN_HD void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) { mac_fp2_inl(A, x, y); }
 #endif
-BN_HD_NOINLINE Fp2 reduce2_wide(const Wide& a0, const Wide& a1) { return Fp2{mont_reduce<MQ, 4>(a0), mont_reduce<MQ, 4>(a1)}; }
+BN_HD_NOINLINE Fp2 reduce2_wide(Wide a0, Wide a1) { return Fp2{mont_reduce<MQ, 4>(a0), mont_reduce<MQ, 4>(a1)}; }
 BN_HD Fp2 reduce2(const AccK& A) {
     Wide a0, a1;
     acck_finish(A, a0, a1);
@@ -125,7 +129,7 @@ BN_HD Fp2 hx_conj(const Ctx& c, const Fp2& a) {
 
 // dense product.  reference src/fields/fq12.rs:295-307
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_mul(const Ctx& c, const Fp2& a, const Fp2& b) {
+BN_HD_NOINLINE Fp2 hx_mul(const Ctx c, Fp2 a, Fp2 b) {
     const int k = c.k();
     Fp2 xa = fp2_mul_xi_shared(a);
     AccK acc;
@@ -148,7 +152,7 @@ BN_HD_NOINLINE Fp2 hx_mul(const Ctx& c, const Fp2& a, const Fp2& b) {
 //   round 2   : even lanes a_i^2, odd lanes their third cross term
 //   round 3   : even lanes xi * a_j^2, odd lanes idle
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_sqr(const Ctx& c, const Fp2& a) {
+BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
     const int k = c.k();
     Fp2 xa = fp2_mul_xi_shared(a);
     Fp2 d = fp2_dbl(fp2_select(k >= 4, xa, a));  // doubled operand: 2 a_k on lanes 0..3, 2 xi a_k on lanes 4,5
@@ -177,7 +181,7 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx& c, const Fp2& a) {
 // product with the sparse line l0 + l3 w^3 + l4 w^4 (reference mul_by_024, src/fields/fq12.rs:107-176).
 // l3k / l4k are ALREADY the variant this lane needs:  l3k = (k < 3 ? xi*l3 : l3), l4k = (k < 4 ? xi*l4 : l4).
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx& c, const Fp2& a, const Fp2& l0, const Fp2& l3k, const Fp2& l4k) {
+BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, Fp2 l0, Fp2 l3k, Fp2 l4k) {
     const int k = c.k();
     AccK acc;
     acck_init(acc);
@@ -194,7 +198,7 @@ BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx& c, const Fp2& a, const Fp2& l0, const 
 
 // product with an Fq6 element m0 + m1 v + m2 v^2 = m0 + m1 w^2 + m2 w^4 known to every lane.
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx& c, const Fp2& a, const Fp2& m0, const Fp2& m1, const Fp2& m2) {
+BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx c, Fp2 a, Fp2 m0, Fp2 m1, Fp2 m2) {
     const int k = c.k();
     Fp2 m1k = fp2_select(k < 2, fp2_mul_xi_shared(m1), m1);
     Fp2 m2k = fp2_select(k < 4, fp2_mul_xi_shared(m2), m2);
@@ -224,7 +228,7 @@ BN_HD Fp2 hx_frob(const Ctx& c, const Fp2& a, int p) {
 // (0,3), (1,4), (2,5).  Each pair is squared with one Fq2 product per lane
 //   (x + y s)^2 = [(x+y)(x + xi y) - xy - xi xy] + [2xy] s .
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx& c, const Fp2& a) {
+BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     const int k = c.k();
     const bool pre = (k & 1) == 0;  // lanes 0,2,4 form (x+y)(x+xi y); lanes 3,5,1 form x*y
     // pair assignment: lane0,3 <- (g0,g3); lane2,5 <- (g1,g4); lane4,1 <- (g2,g5)
@@ -261,7 +265,7 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx& c, const Fp2& a) {
 // 17 + 1 multiplications instead of the reference's 62 + 27.  Gt is canonical, so any addition chain for the same
 // exponent gives the same bytes.
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_exp_by_neg_z(const Ctx& c, const Fp2& a) {
+BN_HD_NOINLINE Fp2 hx_exp_by_neg_z(const Ctx c, Fp2 a) {
     Fp2 a3 = hx_mul(c, hx_cyc_sqr(c, a), a);
     Fp2 res = a;  // leading digit is +1
     for (int b = BN_U_WNAF_LEN - 2; b >= 0; b--) {
@@ -279,7 +283,7 @@ BN_HD_NOINLINE Fp2 hx_exp_by_neg_z(const Ctx& c, const Fp2& a) {
 // f^-1 = conj(f) * N^-1 with N = f * conj(f) in Fq6; the small Fq6/Fq2/Fq inversion chain is done
 // redundantly by every lane (it is a handful of Fq2 products next to one Fq inversion).
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_inv(const Ctx& c, const Fp2& f) {
+BN_HD_NOINLINE Fp2 hx_inv(const Ctx c, Fp2 f) {
     Fp2 fc = hx_conj(c, f);
     Fp2 n = hx_mul(c, f, fc);  // odd coefficients are zero
     Fp2 n0 = c.shfl(n, 0), n1 = c.shfl(n, 2), n2 = c.shfl(n, 4);

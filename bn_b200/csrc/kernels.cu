@@ -334,6 +334,17 @@ k_gt_mul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_
     if (h.active) st_fp2(out + h.pidx * 96 + slot, r);
 }
 
+// Gt::inverse (reference src/lib.rs:172 -> Fq12::inverse, src/fields/fq12.rs:284-292); b is unused.
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
+k_gt_inv(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n) {
+    __shared__ HexSmem smem;
+    HexIndex h = hex_index(n, &smem);
+    const int slot = 16 * gt_slot(h.ctx.kk);
+    Fp2 x = ld_fp2(a + h.pidx * 96 + slot);
+    Fp2 r = hx_inv(h.ctx, x);
+    if (h.active) st_fp2(out + h.pidx * 96 + slot, r);
+}
+
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
 k_gt_pow(const uint32_t* __restrict__ a, const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
     __shared__ HexSmem smem;
@@ -561,6 +572,11 @@ DEFINE_BINARY(g1_mul, k_g1_mul, bn_g1, bn_fr, bn_g1, 128, 128)
 DEFINE_BINARY(g2_mul, k_g2_mul, bn_g2, bn_fr, bn_g2, 128, 128)
 DEFINE_BINARY(gt_pow, k_gt_pow, bn_gt, bn_fr, bn_gt, HEX_WARPS_PER_BLOCK* HEX_PER_WARP, 32 * HEX_WARPS_PER_BLOCK)
 DEFINE_BINARY(gt_mul, k_gt_mul, bn_gt, bn_gt, bn_gt, HEX_WARPS_PER_BLOCK* HEX_PER_WARP, 32 * HEX_WARPS_PER_BLOCK)
+DEFINE_BINARY(gt_inv2, k_gt_inv, bn_gt, bn_gt, bn_gt, HEX_WARPS_PER_BLOCK* HEX_PER_WARP, 32 * HEX_WARPS_PER_BLOCK)
+int bn_b200_gt_inv_batch(const bn_gt* a, bn_gt* out, size_t n) { return bn_b200_gt_inv2_batch(a, a, out, n); }
+int bn_b200_gt_inv_batch_dev(const bn_gt* d_a, bn_gt* d_out, size_t n, void* stream) {
+    return bn_b200_gt_inv2_batch_dev(d_a, d_a, d_out, n, stream);
+}
 
 static int fq_chain_launch(const void* a, const void* b, void* o, size_t n, uint32_t iters, cudaStream_t st) {
     if (n == 0) return 0;

@@ -45,6 +45,11 @@ struct Gt {
     bn_gt v;
     bool operator==(const Gt& o) const { return std::memcmp(&v, &o.v, sizeof v) == 0; }
     bool operator!=(const Gt& o) const { return !(*this == o); }
+    Gt inverse() const {  // Gt::inverse, src/lib.rs:172
+        Gt r;
+        check(bn_b200_gt_inv_batch(&v, &r.v, 1));
+        return r;
+    }
     Gt pow(const Fr& k) const {  // Gt::pow, src/lib.rs:171
         Gt r;
         check(bn_b200_gt_pow_batch(&v, &k.v, &r.v, 1));

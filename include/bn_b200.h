@@ -69,6 +69,10 @@ int bn_b200_gt_pow_batch_dev(const bn_gt* d_a, const bn_fr* d_k, bn_gt* d_out, s
 int bn_b200_gt_mul_batch(const bn_gt* a, const bn_gt* b, bn_gt* out, size_t n);
 int bn_b200_gt_mul_batch_dev(const bn_gt* d_a, const bn_gt* d_b, bn_gt* d_out, size_t n, void* stream);
 
+/* out[i] = a[i].inverse() (a[i] != 0).                 replaces Gt::inverse, src/lib.rs:172 */
+int bn_b200_gt_inv_batch(const bn_gt* a, bn_gt* out, size_t n);
+int bn_b200_gt_inv_batch_dev(const bn_gt* d_a, bn_gt* d_out, size_t n, void* stream);
+
 /* x <- x * b (Montgomery, mod q) repeated `iters` times per element: the BASELINE config-2 microbenchmark of
  * the innermost operation (Fq Mul, src/fields/fp.rs:137-146 -> U256::mul src/arith.rs:257-263). a, b, out: n x 4 u64. */
 int bn_b200_fq_mul_chain(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, uint32_t iters);

@@ -107,11 +107,15 @@ def test_gt_mul_pow(bn):
         k[i] = util.fr_img(s)
     assert np.array_equal(bn.gt_mul_batch(gt, gt[::-1].copy()), cref.gt_mul_batch(gt, gt[::-1].copy(), 8))
     assert np.array_equal(bn.gt_pow_batch(gt, k), cref.gt_pow_batch(gt, k, 8))
+    assert np.array_equal(bn.gt_inv_batch(gt), np.concatenate([cref.fq12_inv(x[None]) for x in gt]))
+    one = util.gt_img(o.FQ12_ONE)
+    assert (bn.gt_mul_batch(gt, bn.gt_inv_batch(gt)) == one[None]).all()
     # non-cyclotomic operand
     f = util.load_json("fq12_kat.json")
     s = util.gt_img(o.fq12_from_flat(f["vector_start"]))[None]
     assert np.array_equal(bn.gt_mul_batch(s, s), cref.fq12_mul(s, s))
     assert np.array_equal(bn.gt_pow_batch(s, k[5:6]), cref.gt_pow_batch(s, k[5:6]))
+    assert np.array_equal(bn.gt_inv_batch(s), cref.fq12_inv(s))
 
 
 def test_bilinearity_on_gpu(bn):
