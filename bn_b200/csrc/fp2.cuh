@@ -39,6 +39,72 @@ BN_HD Fp2 g2_coeff_b() {  // 3/xi, reference src/groups/mod.rs:392-397
     }
     return r;
 }
+// 1/x (Montgomery in, Montgomery out) by the binary extended Euclid of reference src/arith.rs:281-327, followed by
+// the same R^3 fix-up as reference src/fields/fp.rs:103-112.  Data-dependent loops: meant for ONE thread
+// (block_batch_inv in kernels.cu), where it is ~3x shorter than the Fermat chain fp_inv; never call it warp-wide.
+BN_HD_NOINLINE Fp fq_inv_euclid(Fp x) {
+    uint32_t u[8], v[8], b[8], c[8], p[8], t[8];
+    load_mod<MQ>(p);
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) {
+        u[i] = x.v[i];
+        v[i] = p[i];
+        b[i] = i == 0 ? 1u : 0u;
+        c[i] = 0u;
+    }
+    auto is_one = [](const uint32_t* a) {
+        uint32_t o = a[0] ^ 1u;
+        BN_UNROLL
+        for (int i = 1; i < 8; i++) o |= a[i];
+        return o == 0;
+    };
+    auto shr1 = [](uint32_t* a) {
+        BN_UNROLL
+        for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+        a[7] >>= 1;
+    };
+    auto halve_mod = [&](uint32_t* a) {  // a/2 mod p for a < p
+        if (a[0] & 1u) (void)addi8(a, p);  // < 2p < 2^255
+        shr1(a);
+    };
+    auto sub_mod = [&](uint32_t* a, const uint32_t* s) {  // a = a - s mod p
+        uint32_t bw = sub8(t, a, s);
+        BN_UNROLL
+        for (int i = 0; i < 8; i++) a[i] = t[i];
+        if (bw) (void)addi8(a, p);
+    };
+    int guard = 0;
+    while (!is_one(u) && !is_one(v) && guard++ < 1024) {
+        while (!(u[0] & 1u)) {
+            shr1(u);
+            halve_mod(b);
+        }
+        while (!(v[0] & 1u)) {
+            shr1(v);
+            halve_mod(c);
+        }
+        uint32_t bw = sub8(t, u, v);  // u >= v ?
+        if (!bw) {
+            BN_UNROLL
+            for (int i = 0; i < 8; i++) u[i] = t[i];
+            sub_mod(b, c);
+        } else {
+            (void)sub8(t, v, u);
+            BN_UNROLL
+            for (int i = 0; i < 8; i++) v[i] = t[i];
+            sub_mod(c, b);
+        }
+    }
+    Fp r, r3;
+    const bool use_b = is_one(u);
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) {
+        r.v[i] = use_b ? b[i] : c[i];
+        r3.v[i] = FQ_R3_f(i);
+    }
+    return fp_mul<MQ>(r, r3);
+}
+
 BN_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
 BN_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
 BN_HD Fp2 fp2_select(bool c, const Fp2& a, const Fp2& b) {

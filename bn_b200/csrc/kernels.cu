@@ -59,7 +59,7 @@ struct HexSmem {
     Fp pre[HEX_PER_BLOCK];
 };
 
-// 1/x for one x per "slot" of a thread block with ONE Fermat chain (Montgomery's simultaneous inversion):
+// 1/x for one x per "slot" of a thread block with ONE inversion (Montgomery's simultaneous inversion):
 // prefix products, invert the total, peel back.  Collective over the whole block (two __syncthreads); the chain
 // runs on one thread while the other warps of the block yield their issue slots to the SM's other blocks.
 // wslot: slot this thread writes (-1: none); rslot: slot it reads back (-1: slot 0, value unused).
@@ -75,7 +75,7 @@ __device__ __noinline__ Fp block_batch_inv(const Fp& x, int wslot, int rslot, in
             acc = fp_mul<MQ>(acc, val[i]);
             pre[i] = acc;
         }
-        Fp t = fp_inv<MQ>(acc);
+        Fp t = fq_inv_euclid(acc);  // single thread: the divergent binary Euclid is ~3x shorter than Fermat here
         for (int i = nslots - 1; i > 0; i--) {
             Fp vi = val[i];
             val[i] = fp_mul<MQ>(t, pre[i - 1]);

@@ -10,7 +10,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../bn_b200/csrc/pairing.cuh"
+#include "../../bn_b200/csrc/pairing.cuh"  // pulls in fp.cuh, fp2.cuh, duo.cuh, curve.cuh, hexad.cuh
 
 using namespace bn;
 
@@ -134,6 +134,7 @@ void emu_fp_op(int op, int which, const uint64_t* a, const uint64_t* b, uint64_t
             case 3: r = fp_neg<ModQ>(x); break;
             case 4: r = fp_inv<ModQ>(x); break;
             case 5: r = fp_half<ModQ>(x); break;
+            case 7: r = fq_inv_euclid(x); break;
             default: r = fp_from_mont<ModQ>(x); break;
         }
     } else {

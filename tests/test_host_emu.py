@@ -41,6 +41,9 @@ def test_fp_ops(which, p):
         assert _int(emu.fp_op(6, which, _w(a))) == a * rinv % p
     for a in [1, 2, p - 1] + [rnd.randrange(1, p) for _ in range(6)]:
         assert _int(emu.fp_op(4, which, _w(a))) == pow(a * rinv % p, -1, p) * o.MONT_R % p
+    if which == 0:  # binary-Euclid inversion used by the single-thread batched-inversion step
+        for a in [1, 2, 3, p - 1, p - 2, 2**253, (p + 1) // 2] + [rnd.randrange(1, p) for _ in range(200)]:
+            assert _int(emu.fp_op(7, 0, _w(a))) == pow(a * rinv % p, -1, p) * o.MONT_R % p
 
 
 def test_fp2_ops():
