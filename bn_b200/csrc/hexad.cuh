@@ -15,10 +15,16 @@
 // reference's Karatsuba tower (src/fields/fq12.rs:275-307, src/fields/fq6.rs:113-158) which computes the same
 // ring element.
 //
+// Operand exchange: each lane owns three 64-byte slots in shared memory (c.put / c.get, ordered by c.sync ==
+// __syncwarp: a hexad never spans warps).  A lane publishes a_k, xi*a_k and b_k once per operation and every round
+// reads the operand it needs straight from the owner's slot -- the receiver picks the xi / doubled variant by
+// address, so the round loop has no shuffles and no selects, and a, xi*a, b do not occupy registers while the
+// 512-bit accumulators are live.
+//
 // All functions are collective over the hexad: every lane calls them with its own coefficient.
-// `Ctx` supplies k(), shfl(value, source lane index within the hexad) and inv(Fq element, identical in the six
-// lanes); kernels.cu binds them to __shfl_sync and a block-wide batched inversion, tests/host_emu binds them to a
-// barrier exchange between six host threads and a plain Fermat inversion.
+// `Ctx` supplies k(), put(slot, value), get(source lane index within the hexad, slot), sync() and inv(Fq element,
+// identical in the six lanes); kernels.cu binds them to shared memory + __syncwarp and a block-wide batched
+// inversion, tests/host_emu binds them to a barrier exchange between six host threads and a Fermat inversion.
 #pragma once
 #include "fp2.cuh"
 
@@ -131,17 +137,20 @@ BN_HD Fp2 hx_conj(const Ctx& c, const Fp2& a) {
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul(const Ctx c, Fp2 a, Fp2 b) {
     const int k = c.k();
-    Fp2 xa = fp2_mul_xi_shared(a);
+    c.sync();
+    c.put(0, a);
+    c.put(1, fp2_mul_xi_shared(a));
+    c.put(2, b);
+    c.sync();
     AccK acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int s = 0; s < 6; s++) {
-        // receiver k takes a_j from j = k - s (mod 6); the pair (j, s) wraps past w^5 iff j + s >= 6
-        Fp2 send = fp2_select(k + s >= 6, xa, a);
-        Fp2 x = c.shfl(send, mod6(k + 6 - s));
-        Fp2 y = c.shfl(b, s);
+        // receiver k takes a_j from j = k - s (mod 6); the pair (j, s) wraps past w^5 iff j + s >= 6  <=>  s > k
+        Fp2 x = c.get(mod6(k + 6 - s), s > k ? 1 : 0);
+        Fp2 y = c.get(s, 2);
         mac_fp2(acc, x, y);
     }
     return reduce2(acc);
@@ -154,8 +163,14 @@ BN_HD_NOINLINE Fp2 hx_mul(const Ctx c, Fp2 a, Fp2 b) {
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
     const int k = c.k();
-    Fp2 xa = fp2_mul_xi_shared(a);
-    Fp2 d = fp2_dbl(fp2_select(k >= 4, xa, a));  // doubled operand: 2 a_k on lanes 0..3, 2 xi a_k on lanes 4,5
+    {
+        Fp2 xa = fp2_mul_xi_shared(a);
+        c.sync();
+        c.put(0, a);
+        c.put(1, xa);
+        c.put(2, fp2_dbl(fp2_select(k >= 4, xa, a)));  // doubled operand: 2 a_k on lanes 0..3, 2 xi a_k on lanes 4,5
+        c.sync();
+    }
     AccK acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
@@ -169,9 +184,11 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
         //  r3: xi a3 a3 | - | xi a4 a4 | - | xi a5 a5 | -
         const uint32_t xs = r == 0 ? 0x000005u : r == 1 ? 0x111554u : r == 2 ? 0x324140u : 0x050403u;
         const uint32_t ys = r == 0 ? 0x543211u : r == 1 ? 0x432322u : r == 2 ? 0x225130u : 0x050403u;
-        Fp2 send = fp2_select(r < 2 || (r == 2 && (k == 3 || k == 4)), d, fp2_select(r == 3, xa, a));
-        Fp2 x = c.shfl(send, nib(xs, k));
-        Fp2 y = c.shfl(a, nib(ys, k));
+        const int xsrc = nib(xs, k);
+        // slot: doubled (2) in rounds 0-1 and for sources 3,4 in round 2; plain (0) otherwise in round 2; xi (1) in round 3
+        const int xslot = r < 2 ? 2 : (r == 2 ? ((xsrc == 3 || xsrc == 4) ? 2 : 0) : 1);
+        Fp2 x = c.get(xsrc, xslot);
+        Fp2 y = c.get(nib(ys, k), 0);
         y = fp2_select(r == 3 && (k & 1) != 0, fp2_zero(), y);
         mac_fp2(acc, x, y);
     }
@@ -183,13 +200,16 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, Fp2 l0, Fp2 l3k, Fp2 l4k) {
     const int k = c.k();
+    c.sync();
+    c.put(0, a);
+    c.sync();
     AccK acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int r = 0; r < 3; r++) {
-        Fp2 x = c.shfl(a, mod6(k + (r == 0 ? 0 : r == 1 ? 3 : 2)));  // a_k, a_{k-3}, a_{k-4}
+        Fp2 x = c.get(mod6(k + (r == 0 ? 0 : r == 1 ? 3 : 2)), 0);  // a_k, a_{k-3}, a_{k-4}
         Fp2 y = fp2_select(r == 0, l0, fp2_select(r == 1, l3k, l4k));
         mac_fp2(acc, x, y);
     }
@@ -202,13 +222,16 @@ BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx c, Fp2 a, Fp2 m0, Fp2 m1, Fp2 m2) {
     const int k = c.k();
     Fp2 m1k = fp2_select(k < 2, fp2_mul_xi_shared(m1), m1);
     Fp2 m2k = fp2_select(k < 4, fp2_mul_xi_shared(m2), m2);
+    c.sync();
+    c.put(0, a);
+    c.sync();
     AccK acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int r = 0; r < 3; r++) {
-        Fp2 x = c.shfl(a, mod6(k + (r == 0 ? 0 : r == 1 ? 4 : 2)));  // a_k, a_{k-2}, a_{k-4}
+        Fp2 x = c.get(mod6(k + (r == 0 ? 0 : r == 1 ? 4 : 2)), 0);  // a_k, a_{k-2}, a_{k-4}
         Fp2 y = fp2_select(r == 0, m0, fp2_select(r == 1, m1k, m2k));
         mac_fp2(acc, x, y);
     }
@@ -233,10 +256,13 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     const bool pre = (k & 1) == 0;  // lanes 0,2,4 form (x+y)(x+xi y); lanes 3,5,1 form x*y
     // pair assignment: lane0,3 <- (g0,g3); lane2,5 <- (g1,g4); lane4,1 <- (g2,g5)
     const int lo = nib(0x120120u, k), hi = lo + 3;
-    Fp2 xa = fp2_mul_xi_shared(a);
-    Fp2 x = c.shfl(a, lo);
-    Fp2 y = c.shfl(a, hi);
-    Fp2 xy = c.shfl(xa, hi);
+    c.sync();
+    c.put(0, a);
+    c.put(1, fp2_mul_xi_shared(a));
+    c.sync();
+    Fp2 x = c.get(lo, 0);
+    Fp2 y = c.get(hi, 0);
+    Fp2 xy = c.get(hi, 1);
     Fp2 f0, f1;  // factors, components < 2q
     f0.c0 = fp_add_raw(x.c0, fp_select(pre, y.c0, fp_zero()));
     f0.c1 = fp_add_raw(x.c1, fp_select(pre, y.c1, fp_zero()));
@@ -247,7 +273,9 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     mac_fp2(acc, f0, f1);
     Fp2 r = reduce2(acc);
     // partner product: lane0 <- lane3, lane2 <- lane5, lane4 <- lane1
-    Fp2 tmp = c.shfl(r, nib(0x010503u, k));
+    c.put(2, r);
+    c.sync();
+    Fp2 tmp = c.get(nib(0x010503u, k), 2);
     Fp2 r2 = fp2_add(r, r);
     // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*t5 on lane 1
     Fp2 xo = fp2_mul_xi_shared(fp2_select(pre, tmp, r2));
@@ -286,7 +314,10 @@ template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_inv(const Ctx c, Fp2 f) {
     Fp2 fc = hx_conj(c, f);
     Fp2 n = hx_mul(c, f, fc);  // odd coefficients are zero
-    Fp2 n0 = c.shfl(n, 0), n1 = c.shfl(n, 2), n2 = c.shfl(n, 4);
+    c.sync();
+    c.put(0, n);
+    c.sync();
+    Fp2 n0 = c.get(0, 0), n1 = c.get(2, 0), n2 = c.get(4, 0);
     // Fq6 inverse, reference src/fields/fq6.rs:129-141
     Fp2 t0 = fp2_sub(fp2_sqr(n0), fp2_mul(n1, fp2_mul_xi(n2)));
     Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(n2)), fp2_mul(n0, n1));

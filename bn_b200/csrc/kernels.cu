@@ -53,10 +53,14 @@ __device__ __forceinline__ void st_fp2(uint32_t* p, const Fp2& a) {
 #define HEX_BATCH_INV 1   // final-exponentiation Fq inversion: one Fermat chain per block (1) or per lane (0)
 #endif
 
-// Shared scratch of a hexad block: one Fq slot per hexad + prefix products for the batched inversion.
+// Shared scratch of a hexad block: one Fq slot per hexad + prefix products for the batched inversion, and the
+// operand-exchange area: per lane three 64-byte slots (a, xi*a / aux, b / aux), lane stride padded to 52 words so the
+// six lanes of a hexad hit disjoint bank groups with 128-bit accesses.
+#define HEX_LANE_STRIDE 52
 struct HexSmem {
     Fp val[HEX_PER_BLOCK];
     Fp pre[HEX_PER_BLOCK];
+    alignas(16) uint32_t xch[HEX_WARPS_PER_BLOCK][32 * HEX_LANE_STRIDE];
 };
 
 // 1/x for one x per "slot" of a thread block with ONE inversion (Montgomery's simultaneous inversion):
@@ -88,24 +92,30 @@ __device__ __noinline__ Fp block_batch_inv(const Fp& x, int wslot, int rslot, in
 }
 
 struct DevCtx {
-    int kk, base;
-    int slot;        // hexad index inside the block, or -1 for the two spare lanes of a warp
+    int kk;
+    int slot;          // hexad index inside the block, or -1 for the two spare lanes of a warp
     HexSmem* sm;
+    uint32_t* mine;    // this lane's exchange slots
+    uint32_t* hexbase; // lane 0 of this hexad
     __device__ __forceinline__ int k() const { return kk; }
-    __device__ __forceinline__ Fp2 shfl(const Fp2& v, int src) const {
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ void put(int s, const Fp2& v) const {
+        uint4* p = reinterpret_cast<uint4*>(mine + s * 16);
+        p[0] = make_uint4(v.c0.v[0], v.c0.v[1], v.c0.v[2], v.c0.v[3]);
+        p[1] = make_uint4(v.c0.v[4], v.c0.v[5], v.c0.v[6], v.c0.v[7]);
+        p[2] = make_uint4(v.c1.v[0], v.c1.v[1], v.c1.v[2], v.c1.v[3]);
+        p[3] = make_uint4(v.c1.v[4], v.c1.v[5], v.c1.v[6], v.c1.v[7]);
+    }
+    __device__ __forceinline__ Fp2 get(int src, int s) const {
+        const uint4* p = reinterpret_cast<const uint4*>(hexbase + src * HEX_LANE_STRIDE + s * 16);
+        const uint4 a = p[0], b = p[1], c = p[2], d = p[3];
         Fp2 r;
-        const int lane = base + src;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            r.c0.v[i] = __shfl_sync(0xffffffffu, v.c0.v[i], lane);
-            r.c1.v[i] = __shfl_sync(0xffffffffu, v.c1.v[i], lane);
-        }
+        r.c0.v[0] = a.x; r.c0.v[1] = a.y; r.c0.v[2] = a.z; r.c0.v[3] = a.w;
+        r.c0.v[4] = b.x; r.c0.v[5] = b.y; r.c0.v[6] = b.z; r.c0.v[7] = b.w;
+        r.c1.v[0] = c.x; r.c1.v[1] = c.y; r.c1.v[2] = c.z; r.c1.v[3] = c.w;
+        r.c1.v[4] = d.x; r.c1.v[5] = d.y; r.c1.v[6] = d.z; r.c1.v[7] = d.w;
         return r;
     }
-    // 1/x for the x of every hexad in the block with ONE Fermat chain (Montgomery's simultaneous inversion):
-    // prefix products, invert the total, peel back.  Collective over the whole block (two __syncthreads).
-    // A zero input (only possible for garbage lanes / infinity pairs, whose result is discarded) is replaced by 1
-    // so it cannot poison the other pairings' product.
     __device__ __forceinline__ Fp inv(const Fp& x) const {
 #if HEX_BATCH_INV
         return block_batch_inv(x, kk == 0 ? slot : -1, slot, HEX_PER_BLOCK, sm->val, sm->pre);
@@ -303,9 +313,11 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     const int hex = lane / 6;  // 0..5 (5 = the two spare lanes)
     HexIndex h;
     h.ctx.kk = lane - hex * 6;
-    h.ctx.base = hex * 6;
     h.ctx.slot = hex < HEX_PER_WARP ? warp * HEX_PER_WARP + hex : -1;
     h.ctx.sm = sm;
+    h.ctx.mine = sm->xch[warp] + lane * HEX_LANE_STRIDE;
+    // the two spare lanes (30, 31) write their own slots but read hexad 4's, so every read stays inside the warp's area
+    h.ctx.hexbase = sm->xch[warp] + (hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * 6 * HEX_LANE_STRIDE;
     size_t idx = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP + hex;
     h.active = (hex < HEX_PER_WARP) && (idx < n);
     h.pidx = h.active ? idx : (n - 1);

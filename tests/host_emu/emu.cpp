@@ -33,8 +33,18 @@ struct Barrier {
 };
 
 struct HostHexShared {
-    Fp2 slot[6];
+    Fp2 slot[6][3];
     Barrier bar{6};
+};
+
+struct HostCtx {
+    int kk;
+    HostHexShared* sh;
+    int k() const { return kk; }
+    Fp inv(const Fp& x) const { return fp_inv<ModQ>(x); }
+    void put(int s, const Fp2& v) const { sh->slot[kk][s] = v; }
+    Fp2 get(int src, int s) const { return sh->slot[src][s]; }
+    void sync() const { sh->bar.wait(); }
 };
 
 struct HostDuoShared {
@@ -49,20 +59,6 @@ struct HostDuo {
         sh->slot[hh] = v;
         sh->bar.wait();
         Fp r = sh->slot[hh ^ 1];
-        sh->bar.wait();
-        return r;
-    }
-};
-
-struct HostCtx {
-    int kk;
-    HostHexShared* sh;
-    int k() const { return kk; }
-    Fp inv(const Fp& x) const { return fp_inv<ModQ>(x); }
-    Fp2 shfl(const Fp2& v, int src) const {
-        sh->slot[kk] = v;
-        sh->bar.wait();
-        Fp2 r = sh->slot[src];
         sh->bar.wait();
         return r;
     }
