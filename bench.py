@@ -343,6 +343,14 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None  # dram bytes read+written per launch of the dominant kernel, from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = {"bytes_per_launch": tj["k_miller_fexp"]["dram_read_bytes"] + tj["k_miller_fexp"]["dram_write_bytes"],
+                       "algorithmic_bytes_per_launch": n * (102 * 320 + BYTES_OUT), "source": tj["source"]}
+        except Exception:
+            pass
         line_bytes = 102 * 320
         line = {
             "metric": METRIC, "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
@@ -362,9 +370,12 @@ def main():
                 "bound": "int-imad", "kernel": "k_miller_fexp",
                 "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s (IMAD.WIDE.U32 32x32+64)",
                 "frac": achieved / imad_peak,
-                "peak_source": "measured live: pure IMAD.WIDE.U32 kernel, %d blocks x 256 thr (nominal 148*4*16*1.965e9 = 18.6e12)" % blocks,
+                "peak_source": "measured live, this run: k_imad_peak (pure IMAD.WIDE.U32.X carry chains), %d blocks x 256 thr. "
+                               "IMAD.WIDE issues at 8 lanes/clk/SMSP on B200 (148*4*8*1.965e9 = 9.31e12), half of SURVEY.md's "
+                               "nominal 18.6e12 assumption" % blocks,
+                "frac_of_survey_nominal_18.6T": achieved / 18.6e12,
                 "algorithmic": "%d Fq mults/pairing x 136 IMAD in this kernel (whole pairing: %d)" % (M_MILLER_FEXP, M_PAIRING),
-                "traffic": None,
+                "traffic": traffic,
                 "kernel_ms": {"k_pair_lines": ms_lines, "k_miller_fexp": ms_miller},
                 "whole_path_frac": (n / ((ms_lines + ms_miller) * 1e-3)) * M_PAIRING * IMAD_PER_M / imad_peak,
                 "hbm": {"achieved_gbs": n * (BYTES_IN + BYTES_OUT) / (ms_step * 1e-3) / 1e9,

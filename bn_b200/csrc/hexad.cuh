@@ -40,7 +40,7 @@ namespace bn {
 // IMAD.WIDE is the scarce resource on B200 (quarter-rate), the ~170 IADD3 per step ride on the ALU pipe.
 // ------------------------------------------------------------------------------------------------
 #ifndef BN_ACC3
-#define BN_ACC3 1   // measured: 7.87 ms vs 8.06 ms for the merged-accumulator variant (profiles/README.md, run 7)
+#define BN_ACC3 0   // three carry-save accumulators (1) vs two merged 512-bit accumulators (0): within 1 % of each other (profiles/README.md, runs 7-10)
 #endif
 #if BN_ACC3
 // Variant: three carry-save accumulators (P0 = sum x0 y0, P1 = sum x1 y1, P2 = sum (x0+x1)(y0+y1)); the round loop is

@@ -57,10 +57,21 @@ __device__ __forceinline__ void st_fp2(uint32_t* p, const Fp2& a) {
 // operand-exchange area: per lane three 64-byte slots (a, xi*a / aux, b / aux), lane stride padded to 52 words so the
 // six lanes of a hexad hit disjoint bank groups with 128-bit accesses.
 #define HEX_LANE_STRIDE 52
+#ifndef BN_LINE_TMA
+#define BN_LINE_TMA 1   // stream the line coefficients HBM -> shared memory with cp.async.bulk (TMA) one step ahead
+#endif
+#define HEX_LINE_BYTES (HEX_PER_WARP * BN_LINE_WORDS * 4)   // one Miller step of one warp: 5 x 320 B, contiguous in HBM
+struct alignas(128) LineRing {
+    uint32_t buf[2][HEX_PER_WARP * BN_LINE_WORDS];
+    unsigned long long bar[2];
+};
 struct HexSmem {
     Fp val[HEX_PER_BLOCK];
     Fp pre[HEX_PER_BLOCK];
     alignas(16) uint32_t xch[HEX_WARPS_PER_BLOCK][32 * HEX_LANE_STRIDE];
+#if BN_LINE_TMA
+    LineRing ring[HEX_WARPS_PER_BLOCK];
+#endif
 };
 
 // 1/x for one x per "slot" of a thread block with ONE inversion (Montgomery's simultaneous inversion):
@@ -136,6 +147,70 @@ struct DevLineSrc {
         l4k = ld_fp2(L + (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4));
     }
 };
+#if BN_LINE_TMA
+// Line source fed by the TMA engine: one elected lane per warp issues a 1600-byte cp.async.bulk for Miller step t+2
+// as soon as the warp has consumed step t; completion is tracked by an mbarrier transaction count, consumers spin on
+// mbarrier.try_wait.parity (bounded, then trap: a protocol bug must fail the launch, not hang the GPU).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct DevLineSrcTma {
+    const uint32_t* gbase;  // lines + p0 * 80 words (row 0 of this warp's five pairings)
+    size_t row_words;       // n * 80
+    LineRing* ring;
+    int hexc;               // hexad index clamped to 0..4
+    int lane;
+    __device__ __forceinline__ void init() const {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring->bar[0])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring->bar[1])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        issue(0);
+        issue(1);
+    }
+    __device__ __forceinline__ void issue(int t) const {
+        if (lane == 0) {
+            const uint32_t bar = smem_u32(&ring->bar[t & 1]);
+            const uint32_t dst = smem_u32(&ring->buf[t & 1][0]);
+            const uint32_t* src = gbase + (size_t)t * row_words;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)HEX_LINE_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src), "r"((uint32_t)HEX_LINE_BYTES), "r"(bar)
+                         : "memory");
+        }
+    }
+    __device__ __forceinline__ void get(int t, int k, Fp2& l0, Fp2& l3k, Fp2& l4k) const {
+        const uint32_t bar = smem_u32(&ring->bar[t & 1]);
+        const uint32_t parity = (uint32_t)(t >> 1) & 1u;
+        uint32_t ok = 0;
+        for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok)
+                         : "r"(bar), "r"(parity)
+                         : "memory");
+        }
+        if (!ok) __trap();
+        const uint32_t* L = &ring->buf[t & 1][hexc * BN_LINE_WORDS];
+        auto lds2 = [](const uint32_t* p) {
+            const uint4* q = reinterpret_cast<const uint4*>(p);
+            const uint4 a = q[0], b = q[1], c = q[2], d = q[3];
+            Fp2 r;
+            r.c0.v[0] = a.x; r.c0.v[1] = a.y; r.c0.v[2] = a.z; r.c0.v[3] = a.w;
+            r.c0.v[4] = b.x; r.c0.v[5] = b.y; r.c0.v[6] = b.z; r.c0.v[7] = b.w;
+            r.c1.v[0] = c.x; r.c1.v[1] = c.y; r.c1.v[2] = c.z; r.c1.v[3] = c.w;
+            r.c1.v[4] = d.x; r.c1.v[5] = d.y; r.c1.v[6] = d.z; r.c1.v[7] = d.w;
+            return r;
+        };
+        l0 = lds2(L + BN_LINE_OFF_L0);
+        l3k = lds2(L + (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3));
+        l4k = lds2(L + (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4));
+        __syncwarp();  // every lane has read buffer t&1 -> it can be refilled
+        if (t + 2 < BN_NUM_LINES) issue(t + 2);
+    }
+};
+#endif
+
 struct DevLineSink {
     uint32_t* base;
     size_t n, pidx;
@@ -329,7 +404,17 @@ __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
 k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
     __shared__ HexSmem smem;
     HexIndex h = hex_index(n, &smem);
+#if BN_LINE_TMA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    size_t p0 = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP;
+    if (p0 >= n) p0 = n >= HEX_PER_WARP ? n - HEX_PER_WARP : 0;  // warp with no real pairing: any valid rows will do
+    const int hex = lane / 6;
+    DevLineSrcTma src{lines + p0 * BN_LINE_WORDS, n * (size_t)BN_LINE_WORDS, &smem.ring[warp],
+                      hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1, lane};
+    src.init();
+#else
     DevLineSrc src{lines, n, h.pidx};
+#endif
     Fp2 f = hx_miller_loop(h.ctx, src);
     f = hx_final_exp(h.ctx, f);
     if (!flags[h.pidx]) f = hx_one(h.ctx);  // infinity => Gt::one(), reference src/groups/mod.rs:765-766
@@ -434,7 +519,8 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t 
         if (g.lines) cudaFree(g.lines);
         g.lines = nullptr;
         g.lines_cap = 0;
-        cudaError_t e = cudaMalloc(&g.lines, n * (size_t)BN_NUM_LINES * BN_LINE_WORDS * 4);
+        cudaError_t e = cudaMalloc(&g.lines, n * (size_t)BN_NUM_LINES * BN_LINE_WORDS * 4 + 4096);  // + slack: the TMA prefetch of a
+                                                                                                    // partly filled last warp reads 5 pairings
         if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc(line buffer)", e);
         g.lines_cap = n;
     }
