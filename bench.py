@@ -299,6 +299,21 @@ def main():
     fq_mul_rate = nf * chain / (a0.elapsed_time(a1) * 1e-3)
     del fa, fb, fo
 
+    # ---- config 3: 2^16 batched G1 scalar multiplications (random Fr), device resident
+    n3 = 1 << 16
+    k3 = torch.from_numpy(splitmix_scalars(0xB2000003, 4096).view(np.int64)).to(dev).repeat(n3 // 4096, 1)
+    p3 = d_g1.repeat(n3 // n, 1) if n3 >= n else d_g1[:n3]
+    o3 = torch.empty_like(p3)
+    chk(lib.bn_b200_g1_mul_batch_dev(dptr(p3), dptr(k3), dptr(o3), ctypes.c_size_t(n3), sp))
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    chk(lib.bn_b200_g1_mul_batch_dev(dptr(p3), dptr(k3), dptr(o3), ctypes.c_size_t(n3), sp))
+    a1.record(stream)
+    torch.cuda.synchronize()
+    g1_mul_rate = n3 / (a0.elapsed_time(a1) * 1e-3)
+    del k3, p3, o3
+
     # ---- e2e: the host-buffer C ABI call a bn-crate user would make; pinned host buffers, H2D+D2H in the timed region
     h_g1 = torch.empty((n, 12), dtype=torch.int64).pin_memory()
     h_g2 = torch.empty((n, 24), dtype=torch.int64).pin_memory()
@@ -381,6 +396,7 @@ def main():
                 "hbm": {"achieved_gbs": n * (BYTES_IN + BYTES_OUT) / (ms_step * 1e-3) / 1e9,
                         "with_line_buffer_gbs": n * (BYTES_IN + BYTES_OUT + 2 * line_bytes) / (ms_step * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "of": "measured" if peaks else "fallback"},
+                "g1_scalar_mul": {"config": "2^16 G1 * Fr, random scalars (BASELINE config 3)", "per_s": g1_mul_rate},
                 "fq_mul_chain": {"config": "2^20 lanes x 1024 Montgomery muls (BASELINE config 2)",
                                  "fq_mul_per_s": fq_mul_rate, "imad_frac": fq_mul_rate * IMAD_PER_M / imad_peak},
             },

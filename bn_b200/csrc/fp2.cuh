@@ -154,8 +154,36 @@ BN_HD_NOINLINE Fp2 fp2_sqr(Fp2 a) {
 // scale by an Fq element.   reference src/fields/fq2.rs:63-68
 BN_HD Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return Fp2{fp_mul<MQ>(a.c0, k), fp_mul<MQ>(a.c1, k)}; }
 
-// v (9 limbs, < 16q) -> v mod q by binary conditional subtraction of 8q, 4q, 2q, q.
-BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out) {
+// Multiples k*q, k = 0..15, 9 limbs each (12-word rows): the quotient-estimate reduction below subtracts one row.
+#define BN_KQ_STRIDE 12
+BN_HD void kq_table_fill(uint32_t* tab, int k) {  // fill row k (callers split rows across threads)
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)MQ::m(i) * (uint32_t)k;
+        tab[k * BN_KQ_STRIDE + i] = (uint32_t)c;
+        c >>= 32;
+    }
+    tab[k * BN_KQ_STRIDE + 8] = (uint32_t)c;
+    tab[k * BN_KQ_STRIDE + 9] = tab[k * BN_KQ_STRIDE + 10] = tab[k * BN_KQ_STRIDE + 11] = 0;
+}
+
+// v (9 limbs, < 16q) -> v mod q.  Quotient estimate from the top bits: h = floor(v / 2^251), qhat = floor(h*42/256)
+// satisfies floor(v/q) - 1 <= qhat <= floor(v/q) for v < 16q (q / 2^251 = 6.0477..., 256/42 = 6.095...), so
+// v - qhat*q lies in [0, 2q) and one conditional subtraction finishes.  tab == nullptr: binary search fallback.
+BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out, const uint32_t* tab) {
+    if (tab) {
+        const uint32_t h = (v[8] << 5) | (v[7] >> 27);
+        const uint32_t qhat = (h * 42u) >> 8;
+        const uint32_t* row = tab + qhat * BN_KQ_STRIDE;
+        uint32_t kq[8], t[8];
+        BN_UNROLL
+        for (int i = 0; i < 8; i++) kq[i] = row[i];
+        (void)sub8(t, v, kq);  // the ninth limb of the difference is zero (value < 2q < 2^255)
+        cond_sub_p<MQ>(t);
+        BN_UNROLL
+        for (int i = 0; i < 8; i++) out[i] = t[i];
+        return;
+    }
     BN_UNROLL
     for (int sh = 3; sh >= 0; sh--) {
         uint32_t kq[9], t[9];
@@ -177,7 +205,7 @@ BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out) {
 }
 
 // multiply by xi = 9 + i:  (9x - y) + (9y + x) i.   reference src/fields/fq2.rs:70-72 (a full Fq2 mul there)
-BN_HD_NOINLINE Fp2 fp2_mul_xi(Fp2 a) {
+BN_HD Fp2 fp2_mul_xi_tab(const Fp2& a, const uint32_t* tab) {
     Fp2 r;
     // component 0: 9*a0 + (q - a1)  in (0, 10q];  component 1: 9*a1 + a0 in [0, 10q)
     BN_UNROLL
@@ -194,10 +222,13 @@ BN_HD_NOINLINE Fp2 fp2_mul_xi(Fp2 a) {
         v[8] += c;
         c = addi8(v, addend.v);
         v[8] += c;
-        fp_small_reduce9(v, comp == 0 ? r.c0.v : r.c1.v);
+        fp_small_reduce9(v, comp == 0 ? r.c0.v : r.c1.v, tab);
     }
     return r;
 }
+BN_HD_NOINLINE Fp2 fp2_mul_xi(Fp2 a) { return fp2_mul_xi_tab(a, nullptr); }
+// hexad kernels: reduction rows come from a k*q table in shared memory
+BN_HD_NOINLINE Fp2 fp2_mul_xi_t(Fp2 a, const uint32_t* tab) { return fp2_mul_xi_tab(a, tab); }
 
 // 1/a.   reference src/fields/fq2.rs:125-136.  a != 0.
 BN_HD Fp2 fp2_inv(const Fp2& a) {

@@ -22,8 +22,8 @@
 // 512-bit accumulators are live.
 //
 // All functions are collective over the hexad: every lane calls them with its own coefficient.
-// `Ctx` supplies k(), put(slot, value), get(source lane index within the hexad, slot), sync() and inv(Fq element,
-// identical in the six lanes); kernels.cu binds them to shared memory + __syncwarp and a block-wide batched
+// `Ctx` supplies k(), put(slot, value), get(source lane index within the hexad, slot), sync(), mul_xi(Fq2) and
+// inv(Fq element, identical in the six lanes); kernels.cu binds them to shared memory + __syncwarp and a block-wide batched
 // inversion, tests/host_emu binds them to a barrier exchange between six host threads and a Fermat inversion.
 #pragma once
 #include "fp2.cuh"
@@ -116,7 +116,7 @@ BN_HD Fp2 reduce2(const AccK& A) {
     acck_finish(A, a0, a1);
     return reduce2_wide(a0, a1);
 }
-BN_HD Fp2 fp2_mul_xi_shared(const Fp2& a) { return fp2_mul_xi(a); }  // fp2_mul_xi is itself out of line
+
 
 BN_HD int nib(uint32_t packed, int k) { return (int)((packed >> (4 * k)) & 7u); }
 BN_HD int mod6(int x) { return x >= 6 ? x - 6 : x; }
@@ -139,7 +139,7 @@ BN_HD_NOINLINE Fp2 hx_mul(const Ctx c, Fp2 a, Fp2 b) {
     const int k = c.k();
     c.sync();
     c.put(0, a);
-    c.put(1, fp2_mul_xi_shared(a));
+    c.put(1, c.mul_xi(a));
     c.put(2, b);
     c.sync();
     AccK acc;
@@ -164,7 +164,7 @@ template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
     const int k = c.k();
     {
-        Fp2 xa = fp2_mul_xi_shared(a);
+        Fp2 xa = c.mul_xi(a);
         c.sync();
         c.put(0, a);
         c.put(1, xa);
@@ -220,8 +220,8 @@ BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, Fp2 l0, Fp2 l3k, Fp2 l4k) {
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx c, Fp2 a, Fp2 m0, Fp2 m1, Fp2 m2) {
     const int k = c.k();
-    Fp2 m1k = fp2_select(k < 2, fp2_mul_xi_shared(m1), m1);
-    Fp2 m2k = fp2_select(k < 4, fp2_mul_xi_shared(m2), m2);
+    Fp2 m1k = fp2_select(k < 2, c.mul_xi(m1), m1);
+    Fp2 m2k = fp2_select(k < 4, c.mul_xi(m2), m2);
     c.sync();
     c.put(0, a);
     c.sync();
@@ -258,7 +258,7 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     const int lo = nib(0x120120u, k), hi = lo + 3;
     c.sync();
     c.put(0, a);
-    c.put(1, fp2_mul_xi_shared(a));
+    c.put(1, c.mul_xi(a));
     c.sync();
     Fp2 x = c.get(lo, 0);
     Fp2 y = c.get(hi, 0);
@@ -278,7 +278,7 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     Fp2 tmp = c.get(nib(0x010503u, k), 2);
     Fp2 r2 = fp2_add(r, r);
     // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*t5 on lane 1
-    Fp2 xo = fp2_mul_xi_shared(fp2_select(pre, tmp, r2));
+    Fp2 xo = c.mul_xi(fp2_select(pre, tmp, r2));
     Fp2 t_pre = fp2_sub(fp2_sub(r, tmp), xo);               // t0 / t2 / t4
     Fp2 t_im = fp2_select(k == 1, xo, r2);                   // t1 / t3 / xi*t5
     Fp2 t = fp2_select(pre, t_pre, t_im);

@@ -69,6 +69,7 @@ struct HexSmem {
     Fp val[HEX_PER_BLOCK];
     Fp pre[HEX_PER_BLOCK];
     alignas(16) uint32_t xch[HEX_WARPS_PER_BLOCK][32 * HEX_LANE_STRIDE];
+    alignas(16) uint32_t kq[16 * BN_KQ_STRIDE];  // k*q, k = 0..15 (xi-multiplication reduction rows)
 #if BN_LINE_TMA
     LineRing ring[HEX_WARPS_PER_BLOCK];
 #endif
@@ -109,6 +110,7 @@ struct DevCtx {
     uint32_t* mine;    // this lane's exchange slots
     uint32_t* hexbase; // lane 0 of this hexad
     __device__ __forceinline__ int k() const { return kk; }
+    __device__ __forceinline__ Fp2 mul_xi(const Fp2& a) const { return fp2_mul_xi_t(a, sm->kq); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ void put(int s, const Fp2& v) const {
         uint4* p = reinterpret_cast<uint4*>(mine + s * 16);
@@ -386,6 +388,8 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int hex = lane / 6;  // 0..5 (5 = the two spare lanes)
+    if (threadIdx.x < 16) kq_table_fill(sm->kq, threadIdx.x);
+    __syncthreads();
     HexIndex h;
     h.ctx.kk = lane - hex * 6;
     h.ctx.slot = hex < HEX_PER_WARP ? warp * HEX_PER_WARP + hex : -1;

@@ -42,6 +42,12 @@ struct HostCtx {
     HostHexShared* sh;
     int k() const { return kk; }
     Fp inv(const Fp& x) const { return fp_inv<ModQ>(x); }
+    Fp2 mul_xi(const Fp2& a) const {  // exercise the table-driven reduction the kernels use
+        static uint32_t tab[16 * BN_KQ_STRIDE];
+        static bool init = [] { for (int k = 0; k < 16; k++) kq_table_fill(tab, k); return true; }();
+        (void)init;
+        return fp2_mul_xi_t(a, tab);
+    }
     void put(int s, const Fp2& v) const { sh->slot[kk][s] = v; }
     Fp2 get(int src, int s) const { return sh->slot[src][s]; }
     void sync() const { sh->bar.wait(); }
@@ -155,6 +161,12 @@ void emu_fp2_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
         case 2: r = fp2_mul_xi(x); break;
         case 3: r = fp2_inv(x); break;
         case 4: r = fp2_add(x, y); break;
+        case 6: {
+            static uint32_t tab[16 * BN_KQ_STRIDE];
+            for (int k = 0; k < 16; k++) kq_table_fill(tab, k);
+            r = fp2_mul_xi_t(x, tab);
+            break;
+        }
         default: r = fp2_sub(x, y); break;
     }
     store_fp2(out, r);

@@ -48,12 +48,22 @@ def test_fp_ops(which, p):
 
 def test_fp2_ops():
     edge = [(0, 0), (o.Q - 1, o.Q - 1), (5, 0), (0, o.Q - 1), (1, 1)]
+    # values straddling every multiple of q in 9x - y / 9y + x, to stress the quotient estimate
+    for kq in range(1, 10):
+        for dlt in (-1, 0, 1):
+            x = (kq * o.Q + dlt) * pow(9, -1, o.Q) % o.Q
+            edge.append((x, 0))
+            edge.append((0, x))
+    for i in range(len(edge)):
+        a = edge[i]
+        assert np.array_equal(emu.fp2_op(6, fq2img(a)), fq2img(o.fq2_mul_xi(a))), a
     for i in range(120):
         a = edge[i % 5] if i < 10 else (rnd.randrange(o.Q), rnd.randrange(o.Q))
         b = edge[(i // 2) % 5] if i < 10 else (rnd.randrange(o.Q), rnd.randrange(o.Q))
         assert np.array_equal(emu.fp2_op(0, fq2img(a), fq2img(b)), fq2img(o.fq2_mul(a, b)))
         assert np.array_equal(emu.fp2_op(1, fq2img(a)), fq2img(o.fq2_sqr(a)))
         assert np.array_equal(emu.fp2_op(2, fq2img(a)), fq2img(o.fq2_mul_xi(a)))
+        assert np.array_equal(emu.fp2_op(6, fq2img(a)), fq2img(o.fq2_mul_xi(a)))  # quotient-estimate reduction
         if a != (0, 0):
             assert np.array_equal(emu.fp2_op(3, fq2img(a)), fq2img(o.fq2_inv(a)))
 
