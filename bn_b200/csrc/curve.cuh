@@ -138,13 +138,6 @@ struct Line {
 
 // Fq2 multiplication policies for the line schedule: one thread per pairing, or a lane pair per pairing (duo.cuh).
 struct SoloX {
-    template <int OPA, int OPB>
-    BN_HD Fp2Pair pair(const Fp2& a0, const Fp2& b0, const Fp2& a1, const Fp2& b1) const {
-        Fp2Pair r;
-        r.r0 = OPA == DUO_MUL ? fp2_mul(a0, b0) : OPA == DUO_SQR ? fp2_sqr(a0) : fp2_mul_fp(a0, b0.c0);
-        r.r1 = OPB == DUO_MUL ? fp2_mul(a1, b1) : OPB == DUO_SQR ? fp2_sqr(a1) : fp2_mul_fp(a1, b1.c0);
-        return r;
-    }
     BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const { return fp2_mul(a, b); }
     BN_HD Fp2 sqr(const Fp2& a) const { return fp2_sqr(a); }
     BN_HD Fp2 mul_fp(const Fp2& a, const Fp& k) const { return fp2_mul_fp(a, k); }
@@ -153,10 +146,6 @@ struct SoloX {
 template <class D>
 struct DuoX {
     D d;
-    template <int OPA, int OPB>
-    BN_HD Fp2Pair pair(const Fp2& a0, const Fp2& b0, const Fp2& a1, const Fp2& b1) const {
-        return duo_pair<OPA, OPB>(d, a0, b0, a1, b1);
-    }
     BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const { return duo_mul(d, a, b); }
     BN_HD Fp2 sqr(const Fp2& a) const { return duo_sqr(d, a); }
     BN_HD Fp2 mul_fp(const Fp2& a, const Fp& k) const { return duo_mul_fp(d, a, k); }
@@ -167,60 +156,47 @@ template <class X>
 BN_HD Line make_line(const X& X_, const Fp2& ell_0, const Fp2& ell_vw, const Fp2& ell_vv, const Fp& px, const Fp& py) {
     Line L;
     L.l0 = ell_0;
-    Fp2Pair sc = X_.template pair<DUO_MULFP, DUO_MULFP>(ell_vw, fp2_from_fp(py), ell_vv, fp2_from_fp(px));
-    L.l3 = sc.r0;
-    L.l4 = sc.r1;
+    L.l3 = X_.mul_fp(ell_vw, py);
+    L.l4 = X_.mul_fp(ell_vv, px);
     L.xl3 = X_.mul_xi(L.l3);
     L.xl4 = X_.mul_xi(L.l4);
     return L;
 }
 
-// reference src/groups/mod.rs:612-634 (same formulas; independent products are issued in pairs)
+// reference src/groups/mod.rs:612-634
 template <class X>
 BN_HD_NOINLINE Line line_double(const X& X_, G2Proj& r, const Fp& px, const Fp& py) {
-    Fp2Pair p1 = X_.template pair<DUO_MUL, DUO_SQR>(r.x, r.y, r.y, r.y);               // x*y, y^2
-    Fp2 a = fp2_half(p1.r0);
-    Fp2 b = p1.r1;
-    Fp2Pair p2 = X_.template pair<DUO_SQR, DUO_SQR>(r.z, r.z, fp2_add(r.y, r.z), r.z);  // z^2, (y+z)^2
-    Fp2 c = p2.r0;
+    Fp2 a = fp2_half(X_.mul(r.x, r.y));
+    Fp2 b = X_.sqr(r.y);
+    Fp2 c = X_.sqr(r.z);
     Fp2 d = fp2_add(fp2_add(c, c), c);
-    Fp2Pair p3 = X_.template pair<DUO_MUL, DUO_SQR>(g2_coeff_b(), d, r.x, r.x);         // b'*d, x^2
-    Fp2 e = p3.r0;
-    Fp2 j = p3.r1;
+    Fp2 e = X_.mul(g2_coeff_b(), d);
     Fp2 f = fp2_add(fp2_add(e, e), e);
     Fp2 g = fp2_half(fp2_add(b, f));
-    Fp2 h = fp2_sub(p2.r1, fp2_add(b, c));
+    Fp2 h = fp2_sub(X_.sqr(fp2_add(r.y, r.z)), fp2_add(b, c));
     Fp2 i = fp2_sub(e, b);
-    Fp2Pair p4 = X_.template pair<DUO_SQR, DUO_MUL>(e, e, a, fp2_sub(b, f));            // e^2, a*(b-f)
-    Fp2 e_sq = p4.r0;
-    Fp2Pair p5 = X_.template pair<DUO_SQR, DUO_MUL>(g, g, b, h);                        // g^2, b*h
-    r.x = p4.r1;
-    r.y = fp2_sub(p5.r0, fp2_add(fp2_add(e_sq, e_sq), e_sq));
-    r.z = p5.r1;
+    Fp2 j = X_.sqr(r.x);
+    Fp2 e_sq = X_.sqr(e);
+    r.x = X_.mul(a, fp2_sub(b, f));
+    r.y = fp2_sub(X_.sqr(g), fp2_add(fp2_add(e_sq, e_sq), e_sq));
+    r.z = X_.mul(b, h);
     return make_line(X_, X_.mul_xi(i), fp2_neg(h), fp2_add(fp2_add(j, j), j), px, py);
 }
 
 // reference src/groups/mod.rs:592-610
 template <class X>
 BN_HD_NOINLINE Line line_add(const X& X_, G2Proj& r, const Fp2& bx, const Fp2& by, const Fp& px, const Fp& py) {
-    Fp2Pair p1 = X_.template pair<DUO_MUL, DUO_MUL>(r.z, bx, r.z, by);      // z*bx, z*by
-    Fp2 d = fp2_sub(r.x, p1.r0);
-    Fp2 e = fp2_sub(r.y, p1.r1);
-    Fp2Pair p2 = X_.template pair<DUO_SQR, DUO_SQR>(d, d, e, e);            // d^2, e^2
-    Fp2 f = p2.r0;
-    Fp2 g = p2.r1;
-    Fp2Pair p3 = X_.template pair<DUO_MUL, DUO_MUL>(d, f, r.x, f);          // d*f, x*f
-    Fp2 h = p3.r0;
-    Fp2 i = p3.r1;
-    Fp2Pair p4 = X_.template pair<DUO_MUL, DUO_MUL>(r.z, g, r.z, h);        // z*g, z*h
-    Fp2 j = fp2_sub(fp2_add(p4.r0, h), fp2_add(i, i));
-    Fp2Pair p5 = X_.template pair<DUO_MUL, DUO_MUL>(d, j, e, fp2_sub(i, j));  // d*j, e*(i-j)
-    Fp2Pair p6 = X_.template pair<DUO_MUL, DUO_MUL>(h, r.y, e, bx);         // h*y, e*bx
-    Fp2 dby = X_.mul(d, by);
-    r.x = p5.r0;
-    r.y = fp2_sub(p5.r1, p6.r0);
-    r.z = p4.r1;
-    Fp2 ell_0 = X_.mul_xi(fp2_sub(p6.r1, dby));
+    Fp2 d = fp2_sub(r.x, X_.mul(r.z, bx));
+    Fp2 e = fp2_sub(r.y, X_.mul(r.z, by));
+    Fp2 f = X_.sqr(d);
+    Fp2 g = X_.sqr(e);
+    Fp2 h = X_.mul(d, f);
+    Fp2 i = X_.mul(r.x, f);
+    Fp2 j = fp2_sub(fp2_add(X_.mul(r.z, g), h), fp2_add(i, i));
+    r.x = X_.mul(d, j);
+    r.y = fp2_sub(X_.mul(e, fp2_sub(i, j)), X_.mul(h, r.y));
+    r.z = X_.mul(r.z, h);
+    Fp2 ell_0 = X_.mul_xi(fp2_sub(X_.mul(e, bx), X_.mul(d, by)));
     return make_line(X_, ell_0, d, fp2_neg(e), px, py);
 }
 

@@ -69,47 +69,4 @@ BN_HD_NOINLINE Fp2 duo_mul_xi(const D d, Fp2 a) {
     return duo_join(d, r);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Paired operations: two INDEPENDENT Fq2 operations in one out-of-line call, so the two Montgomery pipelines
-// (products, reductions, the lane swap) interleave in one instruction stream.  The line kernel has at most ~2 warps
-// per scheduler at the headline batch; this doubles the instruction-level parallelism each warp offers.
-// ------------------------------------------------------------------------------------------------
-enum { DUO_MUL = 0, DUO_SQR = 1, DUO_MULFP = 2 };  // MULFP: b.c0 carries the Fq scalar
-struct Fp2Pair {
-    Fp2 r0, r1;
-};
-template <int OP>
-BN_HD Wide duo_wide(bool h, const Fp2& a, const Fp2& b) {
-    Wide t = wide_zero();
-    if (OP == DUO_MUL) {
-        Fp y0 = fp_select(h, b.c1, b.c0);
-        Fp y1 = fp_select(h, b.c0, fp_neg_lazy<MQ>(b.c1));
-        wide_mac2(t, a.c0, y0, a.c1, y1);
-    } else if (OP == DUO_SQR) {
-        Fp x = fp_select(h, a.c0, fp_add_raw(a.c0, a.c1));
-        Fp y = fp_select(h, a.c1, fp_add_raw(a.c0, fp_neg_lazy<MQ>(a.c1)));
-        wide_mac1(t, x, y);
-        Wide t2 = t;
-        wide_dbl(t2);
-        BN_UNROLL
-        for (int i = 0; i < 16; i++) t.w[i] = h ? t2.w[i] : t.w[i];
-    } else {
-        wide_mac1(t, h ? a.c1 : a.c0, b.c0);
-    }
-    return t;
-}
-template <int OPA, int OPB, class D>
-BN_HD_NOINLINE Fp2Pair duo_pair(const D d, Fp2 a0, Fp2 b0, Fp2 a1, Fp2 b1) {
-    const bool h = d.h() != 0;
-    Wide t0 = duo_wide<OPA>(h, a0, b0);
-    Wide t1 = duo_wide<OPB>(h, a1, b1);
-    Fp m0 = mont_reduce<MQ, 2>(t0);
-    Fp m1 = mont_reduce<MQ, 2>(t1);
-    Fp2Pair r;
-    r.r0 = duo_join(d, m0);
-    r.r1 = duo_join(d, m1);
-    return r;
-}
-BN_HD Fp2 fp2_from_fp(const Fp& k) { return Fp2{k, fp_zero()}; }
-
 }  // namespace bn
