@@ -363,10 +363,10 @@ def main():
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tj = json.load(f)
             traffic = {"bytes_per_launch": tj["k_miller_fexp"]["dram_read_bytes"] + tj["k_miller_fexp"]["dram_write_bytes"],
-                       "algorithmic_bytes_per_launch": n * (102 * 320 + BYTES_OUT), "source": tj["source"]}
+                       "algorithmic_bytes_per_launch": n * (lib.bn_b200_num_lines() * 320 + BYTES_OUT), "source": tj["source"]}
         except Exception:
             pass
-        line_bytes = 102 * 320
+        line_bytes = lib.bn_b200_num_lines() * 320
         line = {
             "metric": METRIC, "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -374,7 +374,7 @@ def main():
             "config": {"workload": "2^14 batched optimal-ate pairings per GPU (BASELINE config 4; N=8 is config 5's 2^17)",
                        "pairs_per_gpu": n, "global_pairs": world * n, "parallelism": "dp%d (independent pairs)" % world,
                        "gather": "NCCL all_gather of Gt (384 B/pair)" if world > 1 else "none",
-                       "l2": "256 MiB flush write between steps + 535 MB line buffer streamed per step (> 126 MB L2)",
+                       "l2": "256 MiB flush write between steps + %d MB line buffer streamed per step (> 126 MB L2)" % (n * lib.bn_b200_num_lines() * 320 // 1000000),
                        "inputs": "P=G1::one()*a, Q=G2::one()*b, Jacobian z!=1, seeds 0xB2000004+rank"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": n * BYTES_IN,

@@ -134,7 +134,19 @@ struct Line {
     Fp2 l0, l3, xl3, l4, xl4;
 };
 #define BN_LINE_WORDS 80
-#define BN_NUM_LINES 102
+// Miller-loop schedule: signed-digit (NAF) walk of 6u+2 by default -- 65 doublings + 21 additions/subtractions + the 2
+// Frobenius additions = 88 lines instead of the reference's binary walk (64 + 36 + 2 = 102, src/groups/mod.rs:560-582).
+// Different addition chains change the Miller value only by factors from proper subfields, which the final
+// exponentiation kills, so Gt is identical.  BN_ATE_NAF=0 reproduces the reference's chain exactly (the host-emulator
+// tests use it to compare every line and the unreduced Miller value with the reference's known answers).
+#ifndef BN_ATE_NAF
+#define BN_ATE_NAF 1
+#endif
+#if BN_ATE_NAF
+#define BN_NUM_LINES BN_NUM_LINES_NAF
+#else
+#define BN_NUM_LINES BN_NUM_LINES_BIN
+#endif
 
 // Fq2 multiplication policies for the line schedule: one thread per pairing, or a lane pair per pairing (duo.cuh).
 struct SoloX {
@@ -245,10 +257,19 @@ BN_HD void ate_lines(const X& X_, const Fp& px, const Fp& py, const Fp2& qx, con
     r.y = qy;
     r.z = fp2_one();
     int n = 0;
+#if BN_ATE_NAF
+    const Fp2 nqy = fp2_neg(qy);
+    for (int b = BN_ATE_NAF_DIGITS - 1; b >= 0; b--) {
+        sink(n++, line_double(X_, r, px, py));
+        if (b < 64 && ((BN_ATE_NAF_NZ >> b) & 1ULL))
+            sink(n++, line_add(X_, r, qx, ((BN_ATE_NAF_NEG >> b) & 1ULL) ? nqy : qy, px, py));
+    }
+#else
     for (int b = BN_ATE_NBITS - 1; b >= 0; b--) {
         sink(n++, line_double(X_, r, px, py));
         if ((BN_ATE_BITS >> b) & 1ULL) sink(n++, line_add(X_, r, qx, qy, px, py));
     }
+#endif
     Fp2 q1x = qx, q1y = qy;
     g2_mul_by_q(X_, q1x, q1y);
     Fp2 q2x = q1x, q2y = q1y;

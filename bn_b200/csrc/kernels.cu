@@ -3,7 +3,8 @@
 // Kernel map:
 //   k_fq_mul_chain   K1  Fq Montgomery multiply chain (BASELINE config 2; measures the IMAD roofline)
 //   k_g1_mul/k_g2_mul K3 batched scalar multiplication, one thread per point
-//   k_pair_lines     K4a to_affine (one shared inversion) + the 102 ate lines, one thread per pairing,
+//   k_pair_lines[_duo] K4a to_affine (one shared inversion) + the ate line schedule (88 lines, NAF walk of 6u+2), one
+//                        thread or one lane pair per pairing,
 //                        streamed to HBM in consumption order
 //   k_miller_fexp    K4b Miller accumulation + final exponentiation, one 6-lane hexad per pairing
 //                        (5 pairings per warp), all Fq12 state in registers
@@ -606,6 +607,7 @@ int bn_b200_shutdown(void) {
 
 const char* bn_b200_last_error(void) { return t_err.c_str(); }
 int bn_b200_sm_count(void) { return g.sm_count; }
+int bn_b200_num_lines(void) { return BN_NUM_LINES; }
 unsigned long long bn_b200_launch_count(void) { return g_launches.load(); }
 
 int bn_b200_set_profiling(int enable) {

@@ -1,7 +1,8 @@
 // pairing.cuh -- the Miller-loop accumulation f <- f^2 * line over a hexad, fed by precomputed lines.
 //
-// reference G2Precomp::miller_loop, src/groups/mod.rs:485-520 (bits of 6u+2 below the MSB: square, multiply
-// by the doubling line, and on set bits by the addition line; then the two Frobenius lines).
+// reference G2Precomp::miller_loop, src/groups/mod.rs:485-520 (digits of 6u+2 below the leading one: square, multiply
+// by the doubling line, and on non-zero digits by the addition line; then the two Frobenius lines).  The digit
+// schedule (NAF by default, the reference's binary walk with BN_ATE_NAF=0) is the one ate_lines() emitted.
 #pragma once
 #include "curve.cuh"
 #include "hexad.cuh"
@@ -18,6 +19,18 @@ BN_HD Fp2 hx_miller_loop(const Ctx& c, const LineSrc& src) {
     // plain l3 / l4 variants, see LineSrc::get)
     src.get(t++, c.k(), l0, l3k, l4k);
     Fp2 f = fp2_select(c.k() == 0, l0, fp2_select(c.k() == 3, l3k, fp2_select(c.k() == 4, l4k, fp2_zero())));
+#if BN_ATE_NAF
+    // digit BN_ATE_NAF_DIGITS-1 (= 64) is zero: no addition after the first doubling
+    for (int b = BN_ATE_NAF_DIGITS - 2; b >= 0; b--) {
+        f = hx_sqr(c, f);
+        src.get(t++, c.k(), l0, l3k, l4k);
+        f = hx_mul_line(c, f, l0, l3k, l4k);
+        if ((BN_ATE_NAF_NZ >> b) & 1ULL) {
+            src.get(t++, c.k(), l0, l3k, l4k);
+            f = hx_mul_line(c, f, l0, l3k, l4k);
+        }
+    }
+#else
     if ((BN_ATE_BITS >> (BN_ATE_NBITS - 1)) & 1ULL) {
         src.get(t++, c.k(), l0, l3k, l4k);
         f = hx_mul_line(c, f, l0, l3k, l4k);
@@ -31,6 +44,7 @@ BN_HD Fp2 hx_miller_loop(const Ctx& c, const LineSrc& src) {
             f = hx_mul_line(c, f, l0, l3k, l4k);
         }
     }
+#endif
     for (int e = 0; e < 2; e++) {
         src.get(t++, c.k(), l0, l3k, l4k);
         f = hx_mul_line(c, f, l0, l3k, l4k);

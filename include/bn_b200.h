@@ -48,6 +48,8 @@ int bn_b200_shutdown(void);
 const char* bn_b200_last_error(void);
 /* Number of SMs of the active device (0 before init). */
 int bn_b200_sm_count(void);
+/* Line evaluations per pairing in the library's Miller schedule (88: NAF walk of 6u+2; the reference's binary walk has 102). */
+int bn_b200_num_lines(void);
 
 /* pairing(p, q) for n independent pairs.              replaces bn::pairing, src/lib.rs:181-183
  * (groups::pairing src/groups/mod.rs:764-771: to_affine + precompute + miller_loop + final_exponentiation;

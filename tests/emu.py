@@ -6,20 +6,23 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu")
-_SO = os.path.join(_HERE, "libemu.so")
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(variant: str = "product"):
+    """variant "product": the schedule the kernels ship with (NAF Miller loop);
+    variant "refchain": -DBN_ATE_NAF=0, the reference's binary walk, whose 102 lines and unreduced Miller value can be
+    compared with the reference's known answers."""
+    if variant not in _libs:
+        so = os.path.join(_HERE, "libemu.so" if variant == "product" else "libemu_refchain.so")
         src = os.path.join(_HERE, "emu.cpp")
         csrc = os.path.join(os.path.dirname(_HERE), "..", "bn_b200", "csrc")
         deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".inc"))]
-        if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", *os.environ.get("BN_EMU_FLAGS", "").split(), "-shared", "-fPIC", "-o", _SO, src, "-lpthread"])
-        _lib = ctypes.CDLL(_SO)
-    return _lib
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            flags = os.environ.get("BN_EMU_FLAGS", "").split() + ([] if variant == "product" else ["-DBN_ATE_NAF=0"])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", *flags, "-shared", "-fPIC", "-o", so, src, "-lpthread"])
+        _libs[variant] = ctypes.CDLL(so)
+    return _libs[variant]
 
 
 def _p(a):
@@ -58,20 +61,22 @@ def g2_mul(p, fr):
     return out
 
 
-def lines(g1, g2):
+def lines(g1, g2, variant="product"):
     g1, g2 = _c(g1), _c(g2)
-    out = np.zeros((102, 40), dtype=np.uint64)
+    L = lib(variant)
+    out = np.zeros((L.emu_num_lines(), 40), dtype=np.uint64)
     pa = np.zeros(8, dtype=np.uint64)
     qa = np.zeros(16, dtype=np.uint64)
-    finite = lib().emu_lines(_p(g1), _p(g2), _p(out), _p(pa), _p(qa))
+    finite = L.emu_lines(_p(g1), _p(g2), _p(out), _p(pa), _p(qa))
     return finite, out, pa, qa
 
 
-def lines_duo(g1, g2):
+def lines_duo(g1, g2, variant="product"):
     g1, g2 = _c(g1), _c(g2)
-    o0 = np.zeros((102, 40), dtype=np.uint64)
-    o1 = np.zeros((102, 40), dtype=np.uint64)
-    finite = lib().emu_lines_duo(_p(g1), _p(g2), _p(o0), _p(o1))
+    L = lib(variant)
+    o0 = np.zeros((L.emu_num_lines(), 40), dtype=np.uint64)
+    o1 = np.zeros((L.emu_num_lines(), 40), dtype=np.uint64)
+    finite = L.emu_lines_duo(_p(g1), _p(g2), _p(o0), _p(o1))
     return finite, o0, o1
 
 
@@ -82,15 +87,15 @@ def gt_op(op, a, b=None, arg=0):
     return out
 
 
-def miller(lines_arr):
+def miller(lines_arr, variant="product"):
     l = _c(lines_arr)
     out = np.zeros(48, dtype=np.uint64)
-    lib().emu_miller(_p(l), _p(out))
+    lib(variant).emu_miller(_p(l), _p(out))
     return out
 
 
-def pairing(g1, g2):
+def pairing(g1, g2, variant="product"):
     g1, g2 = _c(g1), _c(g2)
     out = np.zeros(48, dtype=np.uint64)
-    lib().emu_pairing(_p(g1), _p(g2), _p(out))
+    lib(variant).emu_pairing(_p(g1), _p(g2), _p(out))
     return out

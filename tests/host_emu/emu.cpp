@@ -97,7 +97,7 @@ void run_hexad(Fn fn) {
 }
 
 struct HostLineSrc {
-    const uint64_t* lines;  // [102][40] u64
+    const uint64_t* lines;  // [BN_NUM_LINES][40] u64
     void get(int t, int k, Fp2& l0, Fp2& l3k, Fp2& l4k) const {
         const uint64_t* L = lines + (size_t)t * 40;
         l0 = load_fp2(L + BN_LINE_OFF_L0 / 2);
@@ -124,6 +124,9 @@ Jac<Fq2Ops> load_g2(const uint64_t* p) { return Jac<Fq2Ops>{load_fp2(p), load_fp
 }  // namespace
 
 extern "C" {
+
+int emu_num_lines() { return BN_NUM_LINES; }
+int emu_ate_naf() { return BN_ATE_NAF; }
 
 // op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 inv(a), 5 half(a), 6 from_mont(a);  which: 0 Fq, 1 Fr
 void emu_fp_op(int op, int which, const uint64_t* a, const uint64_t* b, uint64_t* out) {
@@ -179,7 +182,7 @@ void emu_g2_mul(const uint64_t* p, const uint64_t* fr, uint64_t* out) {
     Jac<Fq2Ops> r = jac_mul<Fq2Ops>(load_g2(p), load_fp(fr));
     store_fp2(out, r.x); store_fp2(out + 8, r.y); store_fp2(out + 16, r.z);
 }
-// lines: [102][40] u64.  returns 1 if finite, 0 if either input is infinity.
+// lines: [BN_NUM_LINES][40] u64.  returns 1 if finite, 0 if either input is infinity.
 int emu_lines(const uint64_t* g1, const uint64_t* g2, uint64_t* lines, uint64_t* p_affine8, uint64_t* q_affine16) {
     Fp px, py; Fp2 qx, qy;
     SoloX X_;
@@ -238,7 +241,7 @@ void emu_miller(const uint64_t* lines, uint64_t* out) {
 }
 // full pairing through the same code path as the kernels
 void emu_pairing(const uint64_t* g1, const uint64_t* g2, uint64_t* out) {
-    std::vector<uint64_t> lines(102 * 40);
+    std::vector<uint64_t> lines(BN_NUM_LINES * 40);
     int finite = emu_lines(g1, g2, lines.data(), nullptr, nullptr);
     run_hexad([&](HostCtx& c) {
         HostLineSrc src{lines.data()};

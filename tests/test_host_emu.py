@@ -84,8 +84,11 @@ def test_scalar_mul_limb_exact(pairs):
 
 
 def test_line_schedule_matches_precompute(pairs):
+    """With the reference's binary walk (BN_ATE_NAF=0) the kernels' line code reproduces precompute() and the
+    unreduced Miller value exactly (test_prepared_g2 / test_miller_loop granularity)."""
     g1, g2, _ = pairs
-    finite, L, pa, qa = emu.lines(g1[0], g2[0])
+    assert emu.lib("refchain").emu_ate_naf() == 0 and emu.lib("refchain").emu_num_lines() == 102
+    finite, L, pa, qa = emu.lines(g1[0], g2[0], "refchain")
     assert finite == 1
     P = o.g_to_affine(o.FQ, util.img_g1(g1[0]))
     Qa = o.g_to_affine(o.FQ2, util.img_g2(g2[0]))
@@ -97,7 +100,20 @@ def test_line_schedule_matches_precompute(pairs):
         l4 = o.fq2_scale(evv, P[0])
         exp = np.concatenate([fq2img(e0), fq2img(l3), fq2img(o.fq2_mul_xi(l3)), fq2img(l4), fq2img(o.fq2_mul_xi(l4))])
         assert np.array_equal(L[t], exp), t
-    assert np.array_equal(emu.miller(L), util.gt_img(o.miller_loop(co, P)))
+    assert np.array_equal(emu.miller(L, "refchain"), util.gt_img(o.miller_loop(co, P)))
+    assert np.array_equal(emu.pairing(g1[0], g2[0], "refchain"), pairs[2][0])
+
+
+def test_naf_schedule_same_gt(pairs):
+    """The shipped NAF walk (88 lines) changes the unreduced Miller value but not Gt."""
+    g1, g2, gt = pairs
+    assert emu.lib().emu_ate_naf() == 1 and emu.lib().emu_num_lines() == 88
+    _, L, _, _ = emu.lines(g1[0], g2[0])
+    P = o.g_to_affine(o.FQ, util.img_g1(g1[0]))
+    Qa = o.g_to_affine(o.FQ2, util.img_g2(g2[0]))
+    unreduced = emu.miller(L)
+    assert not np.array_equal(unreduced, util.gt_img(o.miller_loop(o.g2_precompute(Qa), P)))
+    assert np.array_equal(emu.gt_op(6, unreduced), gt[0])
 
 
 def test_duo_line_schedule_equals_solo(pairs):
