@@ -71,6 +71,38 @@ def gt_inv_batch(a, device: int = 0) -> np.ndarray:
     return out
 
 
+FR_OPS = {"mul": 0, "add": 1, "sub": 2, "neg": 3, "inverse": 4}
+
+
+def fr_op_batch(op: str, a, b=None, device: int = 0) -> np.ndarray:
+    """Batched Fr arithmetic (reference src/lib.rs:19-54): op in mul/add/sub/neg/inverse."""
+    lib = _lib.init(device)
+    a = _arr(a, FR_WORDS)
+    b = _arr(b, FR_WORDS) if b is not None else None
+    out = np.empty_like(a)
+    _lib.check(lib.bn_b200_fr_op_batch(FR_OPS[op], _p(a), _p(b) if b is not None else None, _p(out),
+                                       ctypes.c_size_t(len(a))))
+    return out
+
+
+def g1_normalize_batch(g1, device: int = 0) -> np.ndarray:
+    """Group::normalize for G1 (reference src/lib.rs:88-95)."""
+    lib = _lib.init(device)
+    g1 = _arr(g1, G1_WORDS)
+    out = np.empty_like(g1)
+    _lib.check(lib.bn_b200_g1_normalize_batch(_p(g1), _p(out), ctypes.c_size_t(len(g1))))
+    return out
+
+
+def g2_normalize_batch(g2, device: int = 0) -> np.ndarray:
+    """Group::normalize for G2 (reference src/lib.rs:131-138)."""
+    lib = _lib.init(device)
+    g2 = _arr(g2, G2_WORDS)
+    out = np.empty_like(g2)
+    _lib.check(lib.bn_b200_g2_normalize_batch(_p(g2), _p(out), ctypes.c_size_t(len(g2))))
+    return out
+
+
 def fq_mul_chain(a, b, iters: int, device: int = 0) -> np.ndarray:
     """x <- x*b (Montgomery mod q) `iters` times per element (BASELINE config 2)."""
     lib = _lib.init(device)

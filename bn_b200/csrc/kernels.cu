@@ -297,6 +297,52 @@ __global__ void __launch_bounds__(128) k_g2_mul(const uint32_t* __restrict__ p, 
     st_fp2(out + i * 48 + 32, r.z);
 }
 
+// ---- rows f-3 / f-4: batched Fr arithmetic and Group::normalize ------------------------------------------------
+// op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 inverse(a) (0 -> 0; the crate returns None, src/fields/fp.rs:103-112)
+__global__ void __launch_bounds__(128) k_fr_op(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                                               uint32_t* __restrict__ out, size_t n, int op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x = ld_fp(a + i * 8), y = (op <= 2) ? ld_fp(b + i * 8) : fp_zero(), r;
+    switch (op) {
+        case 0: r = fp_mul<ModR>(x, y); break;
+        case 1: r = fp_add<ModR>(x, y); break;
+        case 2: r = fp_sub<ModR>(x, y); break;
+        case 3: r = fp_neg<ModR>(x); break;
+        default: r = fp_is_zero(x) ? x : fp_inv<ModR>(x); break;
+    }
+    st_fp(out + i * 8, r);
+}
+// Group::normalize (reference src/lib.rs:88-95, 131-138): affine coordinates with z = one; infinity is left as is.
+__global__ void __launch_bounds__(128) k_g1_normalize(const uint32_t* __restrict__ p, uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x = ld_fp(p + i * 24), y = ld_fp(p + i * 24 + 8), z = ld_fp(p + i * 24 + 16);
+    if (!fp_is_zero(z)) {
+        Fp zi = fp_inv<MQ>(z), zi2 = fp_mul<MQ>(zi, zi);
+        x = fp_mul<MQ>(x, zi2);
+        y = fp_mul<MQ>(y, fp_mul<MQ>(zi2, zi));
+        z = fq_one();
+    }
+    st_fp(out + i * 24, x);
+    st_fp(out + i * 24 + 8, y);
+    st_fp(out + i * 24 + 16, z);
+}
+__global__ void __launch_bounds__(128) k_g2_normalize(const uint32_t* __restrict__ p, uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp2 x = ld_fp2(p + i * 48), y = ld_fp2(p + i * 48 + 16), z = ld_fp2(p + i * 48 + 32);
+    if (!fp2_is_zero(z)) {
+        Fp2 zi = fp2_inv(z), zi2 = fp2_sqr(zi);
+        x = fp2_mul(x, zi2);
+        y = fp2_mul(y, fp2_mul(zi2, zi));
+        z = fp2_one();
+    }
+    st_fp2(out + i * 48, x);
+    st_fp2(out + i * 48 + 16, y);
+    st_fp2(out + i * 48 + 32, z);
+}
+
 // K4a: one thread per pairing.  flags[p] = 1 when the pair is finite, 0 when either point is infinity.
 __global__ void __launch_bounds__(64) k_pair_lines(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
                                                    uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
@@ -718,5 +764,61 @@ int bn_b200_imad_peak_dev(uint32_t* d_scratch, uint32_t blocks, uint32_t iters, 
     CU(cudaGetLastError());
     return 0;
 }
+
+int bn_b200_fr_op_batch_dev(int op, const bn_fr* d_a, const bn_fr* d_b, bn_fr* d_out, size_t n, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (op < 0 || op > 4) return fail(BN_B200_EINVAL, "bad Fr op");
+    if (n && (!d_a || !d_out || (op <= 2 && !d_b))) return fail(BN_B200_EINVAL, "null pointer");
+    if (n == 0) return 0;
+    k_fr_op<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(W(d_a), W(d_b), W(d_out), n, op);
+    g_launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+int bn_b200_fr_op_batch(int op, const bn_fr* a, const bn_fr* b, bn_fr* out, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (op < 0 || op > 4) return fail(BN_B200_EINVAL, "bad Fr op");
+    if (n == 0) return 0;
+    if (!a || !out || (op <= 2 && !b)) return fail(BN_B200_EINVAL, "null pointer");
+    return host_call(a, n * sizeof(bn_fr), b ? b : a, n * sizeof(bn_fr), out, n * sizeof(bn_fr),
+                     [&](void* x, void* y, void* o, cudaStream_t st) {
+                         k_fr_op<<<blocks_for(n, 128), 128, 0, st>>>(W(x), W(y), W(o), n, op);
+                         g_launches += 1;
+                         CU(cudaGetLastError());
+                         return 0;
+                     });
+}
+#define DEFINE_NORMALIZE(NAME, KERNEL, T)                                                                          \
+    int bn_b200_##NAME##_normalize_batch_dev(const T* d_p, T* d_out, size_t n, void* stream) {                      \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
+        int rc = ensure_ready();                                                                                    \
+        if (rc) return rc;                                                                                          \
+        if (n && (!d_p || !d_out)) return fail(BN_B200_EINVAL, "null pointer");                                     \
+        if (n == 0) return 0;                                                                                       \
+        KERNEL<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(W(d_p), W(d_out), n);      \
+        g_launches += 1;                                                                                            \
+        CU(cudaGetLastError());                                                                                     \
+        return 0;                                                                                                   \
+    }                                                                                                               \
+    int bn_b200_##NAME##_normalize_batch(const T* p, T* out, size_t n) {                                            \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
+        int rc = ensure_ready();                                                                                    \
+        if (rc) return rc;                                                                                          \
+        if (n == 0) return 0;                                                                                       \
+        if (!p || !out) return fail(BN_B200_EINVAL, "null pointer");                                                \
+        return host_call(p, n * sizeof(T), p, sizeof(T), out, n * sizeof(T),                                        \
+                         [&](void* x, void*, void* o, cudaStream_t st) {                                            \
+                             KERNEL<<<blocks_for(n, 128), 128, 0, st>>>(W(x), W(o), n);                             \
+                             g_launches += 1;                                                                       \
+                             CU(cudaGetLastError());                                                                \
+                             return 0;                                                                              \
+                         });                                                                                        \
+    }
+DEFINE_NORMALIZE(g1, k_g1_normalize, bn_g1)
+DEFINE_NORMALIZE(g2, k_g2_normalize, bn_g2)
 
 }  // extern "C"

@@ -75,6 +75,18 @@ int bn_b200_gt_mul_batch_dev(const bn_gt* d_a, const bn_gt* d_b, bn_gt* d_out, s
 int bn_b200_gt_inv_batch(const bn_gt* a, bn_gt* out, size_t n);
 int bn_b200_gt_inv_batch_dev(const bn_gt* d_a, bn_gt* d_out, size_t n, void* stream);
 
+/* Batched Fr arithmetic.            replaces bn::Fr Mul/Add/Sub/Neg/inverse, src/lib.rs:25, 32-54
+ * op: 0 a*b, 1 a+b, 2 a-b, 3 -a, 4 a.inverse() (inverse of zero yields zero; the crate returns None).  b may be NULL for op >= 3. */
+int bn_b200_fr_op_batch(int op, const bn_fr* a, const bn_fr* b, bn_fr* out, size_t n);
+int bn_b200_fr_op_batch_dev(int op, const bn_fr* d_a, const bn_fr* d_b, bn_fr* d_out, size_t n, void* stream);
+
+/* Group::normalize for n points (row f-3: the device half of wire encoding: affine x, y with z = one; infinity unchanged).
+ * replaces src/lib.rs:88-95, 131-138 (G::to_affine, src/groups/mod.rs:113-130). */
+int bn_b200_g1_normalize_batch(const bn_g1* p, bn_g1* out, size_t n);
+int bn_b200_g1_normalize_batch_dev(const bn_g1* d_p, bn_g1* d_out, size_t n, void* stream);
+int bn_b200_g2_normalize_batch(const bn_g2* p, bn_g2* out, size_t n);
+int bn_b200_g2_normalize_batch_dev(const bn_g2* d_p, bn_g2* d_out, size_t n, void* stream);
+
 /* x <- x * b (Montgomery, mod q) repeated `iters` times per element: the BASELINE config-2 microbenchmark of
  * the innermost operation (Fq Mul, src/fields/fp.rs:137-146 -> U256::mul src/arith.rs:257-263). a, b, out: n x 4 u64. */
 int bn_b200_fq_mul_chain(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, uint32_t iters);

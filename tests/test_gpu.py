@@ -98,6 +98,46 @@ def test_g2_golden_vectors(bn):
         acc = cref.g2_add(bn.g2_mul_batch(acc, k), acc)
 
 
+def test_fr_golden_vectors_on_gpu(bn):
+    """tests/serialization.rs fr_vectors: acc <- acc*acc + acc + acc^-1, every step computed by the GPU Fr kernels."""
+    lines = util.load_vectors("fr_vectors.txt", 400)
+    acc = util.fr_img(1)[None]
+    for want in lines:
+        assert o.encode_fr(o.fr_from_bytes(acc[0].tobytes())).hex() == want
+        sq = bn.fr_op_batch("mul", acc, acc)
+        acc = bn.fr_op_batch("add", bn.fr_op_batch("add", sq, acc), bn.fr_op_batch("inverse", acc))
+    k = util.synth_scalars(123, 300)
+    k[0] = 0
+    inv = bn.fr_op_batch("inverse", k)
+    assert not inv[0].any()
+    one = util.fr_img(1)
+    assert all(np.array_equal(x, one) for x in bn.fr_op_batch("mul", k[1:], inv[1:]))
+    assert np.array_equal(bn.fr_op_batch("sub", k, k), np.zeros_like(k))
+    assert np.array_equal(bn.fr_op_batch("add", k, bn.fr_op_batch("neg", k)), np.zeros_like(k))
+
+
+def test_normalize_and_wire_vectors(bn):
+    """Group::normalize on the GPU reproduces the reference's 65/129-byte encodings of the golden recurrences."""
+    k = util.fr_img(23938123)[None]
+    for name, gen, mulb, addc, norm_gpu, norm_cpu, enc, img, nvec in (
+            ("g1", cref.g1_generator(), bn.g1_mul_batch, cref.g1_add, bn.g1_normalize_batch, cref.g1_normalize, o.encode_g1, util.img_g1, 40),
+            ("g2", cref.g2_generator(), bn.g2_mul_batch, cref.g2_add, bn.g2_normalize_batch, cref.g2_normalize, o.encode_g2, util.img_g2, 15)):
+        lines = util.load_vectors(name + "_vectors.txt", nvec)
+        acc, accs = gen, []
+        for _ in lines:
+            accs.append(acc[0])
+            acc = addc(mulb(acc, k), acc)
+        accs = np.stack(accs)
+        normed = norm_gpu(accs)
+        assert np.array_equal(normed, np.concatenate([norm_cpu(a[None]) for a in accs]))
+        for row, want in zip(normed, lines):
+            assert enc(img(row)).hex() == want
+    inf1 = util.g1_img(o.g_zero(o.FQ))[None]
+    assert np.array_equal(bn.g1_normalize_batch(inf1), inf1)
+    inf2 = util.g2_img(o.g_zero(o.FQ2))[None]
+    assert np.array_equal(bn.g2_normalize_batch(inf2), inf2)
+
+
 def test_gt_mul_pow(bn):
     n = 23
     g1, g2 = util.synth_pairs(77, n)
