@@ -314,6 +314,18 @@ def main():
     g1_mul_rate = n3 / (a0.elapsed_time(a1) * 1e-3)
     del k3, p3, o3
 
+    # ---- row f-1: fused pairing(...).pow(s), same batch
+    d_pw = torch.empty_like(d_out)
+    chk(lib.bn_b200_pairing_pow_batch_dev(dptr(d_g1), dptr(d_g2), dptr(ka), dptr(d_pw), ctypes.c_size_t(n), sp))
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    chk(lib.bn_b200_pairing_pow_batch_dev(dptr(d_g1), dptr(d_g2), dptr(ka), dptr(d_pw), ctypes.c_size_t(n), sp))
+    a1.record(stream)
+    torch.cuda.synchronize()
+    pairing_pow_rate = n / (a0.elapsed_time(a1) * 1e-3)
+    del d_pw
+
     # ---- e2e: the host-buffer C ABI call a bn-crate user would make; pinned host buffers, H2D+D2H in the timed region
     h_g1 = torch.empty((n, 12), dtype=torch.int64).pin_memory()
     h_g2 = torch.empty((n, 24), dtype=torch.int64).pin_memory()
@@ -396,6 +408,7 @@ def main():
                 "hbm": {"achieved_gbs": n * (BYTES_IN + BYTES_OUT) / (ms_step * 1e-3) / 1e9,
                         "with_line_buffer_gbs": n * (BYTES_IN + BYTES_OUT + 2 * line_bytes) / (ms_step * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "of": "measured" if peaks else "fallback"},
+                "fused_pairing_pow": {"config": "2^14 x pairing(P,Q).pow(s) in one pass (row f-1)", "per_s": pairing_pow_rate},
                 "g1_scalar_mul": {"config": "2^16 G1 * Fr, random scalars (BASELINE config 3)", "per_s": g1_mul_rate},
                 "fq_mul_chain": {"config": "2^20 lanes x 1024 Montgomery muls (BASELINE config 2)",
                                  "fq_mul_per_s": fq_mul_rate, "imad_frac": fq_mul_rate * IMAD_PER_M / imad_peak},

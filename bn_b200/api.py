@@ -42,6 +42,17 @@ def pairing_batch(g1, g2, device: int = 0) -> np.ndarray:
     return _binary("bn_b200_pairing_batch", g1, G1_WORDS, g2, G2_WORDS, GT_WORDS, device)
 
 
+def pairing_pow_batch(g1, g2, fr, device: int = 0) -> np.ndarray:
+    """pairing(g1[i], g2[i]).pow(fr[i]) fused in one pass (reference examples/joux.rs:19-21)."""
+    lib = _lib.init(device)
+    g1, g2, fr = _arr(g1, G1_WORDS), _arr(g2, G2_WORDS), _arr(fr, FR_WORDS)
+    if not (len(g1) == len(g2) == len(fr)):
+        raise ValueError("batch length mismatch")
+    out = np.empty((len(g1), GT_WORDS), dtype=np.uint64)
+    _lib.check(lib.bn_b200_pairing_pow_batch(_p(g1), _p(g2), _p(fr), _p(out), ctypes.c_size_t(len(g1))))
+    return out
+
+
 def g1_mul_batch(g1, fr, device: int = 0) -> np.ndarray:
     """g1[i] * fr[i] (Jacobian, un-normalised like the crate).  reference src/lib.rs:116-120."""
     return _binary("bn_b200_g1_mul_batch", g1, G1_WORDS, fr, FR_WORDS, G1_WORDS, device)

@@ -450,9 +450,11 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     return h;
 }
 
-// K4b: Miller loop + final exponentiation, one hexad per pairing.
-__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
-k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
+// K4b: Miller loop + final exponentiation, one hexad per pairing.  POW: additionally raise the result to the
+// per-pairing scalar k (fused pairing(p, q).pow(k), row f-1).
+template <bool POW>
+__device__ __forceinline__ void miller_fexp_body(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags,
+                                                 const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
     __shared__ HexSmem smem;
     HexIndex h = hex_index(n, &smem);
 #if BN_LINE_TMA
@@ -469,7 +471,20 @@ k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ fl
     Fp2 f = hx_miller_loop(h.ctx, src);
     f = hx_final_exp(h.ctx, f);
     if (!flags[h.pidx]) f = hx_one(h.ctx);  // infinity => Gt::one(), reference src/groups/mod.rs:765-766
+    if (POW) {
+        Fp e = fp_from_mont<ModR>(ld_fp(k + h.pidx * 8));  // U256::from(Fr), reference src/fields/fp.rs:15-22
+        f = hx_pow_cyc(h.ctx, f, e);
+    }
     if (h.active) st_fp2(out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk), f);
+}
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
+k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
+    miller_fexp_body<false>(lines, flags, nullptr, out, n);
+}
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
+k_miller_fexp_pow(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k,
+                  uint32_t* __restrict__ out, size_t n) {
+    miller_fexp_body<true>(lines, flags, k, out, n);
 }
 
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
@@ -564,7 +579,7 @@ inline unsigned blocks_for(size_t n, unsigned per_block) { return (unsigned)((n 
 inline const uint32_t* W(const void* p) { return reinterpret_cast<const uint32_t*>(p); }
 inline uint32_t* W(void* p) { return reinterpret_cast<uint32_t*>(p); }
 
-int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t n, cudaStream_t st) {
+int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
     if (g.lines_cap < n) {
         if (g.lines) cudaFree(g.lines);
@@ -583,8 +598,12 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t 
     else
         k_pair_lines<<<blocks_for(n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
     if (g.profiling) CU(cudaEventRecord(g.ev[1], st));
-    k_miller_fexp<<<blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), 32 * HEX_WARPS_PER_BLOCK, 0, st>>>(
-        g.lines, g.flags, W(d_out), n);
+    if (d_k)
+        k_miller_fexp_pow<<<blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), 32 * HEX_WARPS_PER_BLOCK, 0, st>>>(
+            g.lines, g.flags, W(d_k), W(d_out), n);
+    else
+        k_miller_fexp<<<blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), 32 * HEX_WARPS_PER_BLOCK, 0, st>>>(
+            g.lines, g.flags, W(d_out), n);
     if (g.profiling) {
         CU(cudaEventRecord(g.ev[2], st));
         g.ev_valid = true;
@@ -679,7 +698,7 @@ int bn_b200_pairing_batch_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, 
     int rc = ensure_ready();
     if (rc) return rc;
     if (n && (!d_p || !d_q || !d_out)) return fail(BN_B200_EINVAL, "null pointer");
-    return pairing_dev_locked(d_p, d_q, d_out, n, stream ? (cudaStream_t)stream : g.stream);
+    return pairing_dev_locked(d_p, d_q, nullptr, d_out, n, stream ? (cudaStream_t)stream : g.stream);
 }
 int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -689,8 +708,33 @@ int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n) 
     if (!p || !q || !out) return fail(BN_B200_EINVAL, "null pointer");
     return host_call(p, n * sizeof(bn_g1), q, n * sizeof(bn_g2), out, n * sizeof(bn_gt),
                      [&](void* a, void* b, void* o, cudaStream_t st) {
-                         return pairing_dev_locked((const bn_g1*)a, (const bn_g2*)b, (bn_gt*)o, n, st);
+                         return pairing_dev_locked((const bn_g1*)a, (const bn_g2*)b, nullptr, (bn_gt*)o, n, st);
                      });
+}
+int bn_b200_pairing_pow_batch_dev(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n && (!d_p || !d_q || !d_k || !d_out)) return fail(BN_B200_EINVAL, "null pointer");
+    return pairing_dev_locked(d_p, d_q, d_k, d_out, n, stream ? (cudaStream_t)stream : g.stream);
+}
+int bn_b200_pairing_pow_batch(const bn_g1* p, const bn_g2* q, const bn_fr* k, bn_gt* out, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (!p || !q || !k || !out) return fail(BN_B200_EINVAL, "null pointer");
+    void* d_k = nullptr;
+    cudaError_t e = cudaMalloc(&d_k, n * sizeof(bn_fr));
+    if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc(scalars)", e);
+    e = cudaMemcpyAsync(d_k, k, n * sizeof(bn_fr), cudaMemcpyHostToDevice, g.stream);
+    if (e != cudaSuccess) { cudaFree(d_k); return fail(BN_B200_ECUDA, "cudaMemcpyAsync(scalars)", e); }
+    rc = host_call(p, n * sizeof(bn_g1), q, n * sizeof(bn_g2), out, n * sizeof(bn_gt),
+                   [&](void* a, void* b, void* o, cudaStream_t st) {
+                       return pairing_dev_locked((const bn_g1*)a, (const bn_g2*)b, (const bn_fr*)d_k, (bn_gt*)o, n, st);
+                   });
+    cudaFree(d_k);
+    return rc;
 }
 
 #define DEFINE_BINARY(NAME, KERNEL, TA, TB, TO, PER_BLOCK, THREADS)                                              \

@@ -87,6 +87,13 @@ inline std::vector<Gt> pairing_batch(const std::vector<G1>& p, const std::vector
     check(bn_b200_pairing_batch(&p.data()->v, &q.data()->v, &out.data()->v, p.size()));
     return out;
 }
+// pairing(p[i], q[i]).pow(k[i]) fused on the device (the pattern of reference examples/joux.rs:19-21)
+inline std::vector<Gt> pairing_pow_batch(const std::vector<G1>& p, const std::vector<G2>& q, const std::vector<Fr>& k) {
+    if (p.size() != q.size() || p.size() != k.size()) throw Error(BN_B200_EINVAL, "pairing_pow_batch: length mismatch");
+    std::vector<Gt> out(p.size());
+    check(bn_b200_pairing_pow_batch(&p.data()->v, &q.data()->v, &k.data()->v, &out.data()->v, p.size()));
+    return out;
+}
 inline std::vector<G1> mul_batch(const std::vector<G1>& p, const std::vector<Fr>& k) {
     if (p.size() != k.size()) throw Error(BN_B200_EINVAL, "mul_batch: length mismatch");
     std::vector<G1> out(p.size());

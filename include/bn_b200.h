@@ -57,6 +57,11 @@ int bn_b200_num_lines(void);
 int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n);
 int bn_b200_pairing_batch_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t n, void* stream);
 
+/* out[i] = pairing(p[i], q[i]).pow(k[i]) in one pass (the pattern of reference examples/joux.rs:19-21
+ * and test_binlinearity, src/groups/mod.rs:811).  Same bytes as bn_b200_pairing_batch followed by bn_b200_gt_pow_batch. */
+int bn_b200_pairing_pow_batch(const bn_g1* p, const bn_g2* q, const bn_fr* k, bn_gt* out, size_t n);
+int bn_b200_pairing_pow_batch_dev(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, void* stream);
+
 /* out[i] = p[i] * k[i].                               replaces `impl Mul<Fr> for G1/G2`, src/lib.rs:116-120, 159-163
  * Output is the same un-normalised Jacobian triple the crate produces (src/groups/mod.rs:250-270). */
 int bn_b200_g1_mul_batch(const bn_g1* p, const bn_fr* k, bn_g1* out, size_t n);

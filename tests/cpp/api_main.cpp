@@ -43,6 +43,13 @@ int main(int argc, char** argv) {
             if (e.pow(fr[i]) != want_pow[i]) { fprintf(stderr, "Gt::pow mismatch at %zu\n", i); return 1; }
             if (bn::pairing(sp, g2[i]) != want_pow[i]) { fprintf(stderr, "bilinearity mismatch at %zu\n", i); return 1; }
         }
+        auto fused = bn::pairing_pow_batch(g1, g2, fr);
+        for (size_t i = 0; i < n; i++)
+            if (fused[i] != want_pow[i]) { fprintf(stderr, "pairing_pow_batch mismatch at %zu\n", i); return 1; }
+        if (gt[0].inverse() * gt[0] != bn::pairing(g1[1], g2[1]).pow(fr[1]).inverse() * want_pow[1]) {
+            fprintf(stderr, "Gt::inverse mismatch\n");
+            return 1;
+        }
         auto pw = bn::pow_batch(gt, fr);
         auto mg = bn::mul_batch(g1, fr);
         for (size_t i = 0; i < n; i++) {

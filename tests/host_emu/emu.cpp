@@ -211,7 +211,7 @@ int emu_lines_duo(const uint64_t* g1, const uint64_t* g2, uint64_t* lines_lane0,
     return ok[0] & ok[1];
 }
 // Gt images are bn::Gt layout (48 u64).  op: 0 mul(a,b) 1 sqr 2 cyc_sqr 3 inv 4 frob(p=arg) 5 exp_by_neg_z
-//   6 final_exp 7 conj 8 pow(a, plain exponent b[0..3])
+//   6 final_exp 7 conj 8 pow(a, plain exponent b[0..3]) 9 pow_cyc(a, plain exponent)
 void emu_gt_op(int op, const uint64_t* a, const uint64_t* b, int arg, uint64_t* out) {
     run_hexad([&](HostCtx& c) {
         Fp2 x = load_fp2(a + 8 * gt_slot(c.k()));
@@ -226,6 +226,7 @@ void emu_gt_op(int op, const uint64_t* a, const uint64_t* b, int arg, uint64_t* 
             case 5: r = hx_exp_by_neg_z(c, x); break;
             case 6: r = hx_final_exp(c, x); break;
             case 7: r = hx_conj(c, x); break;
+            case 9: r = hx_pow_cyc(c, x, load_fp(b)); break;
             default: r = hx_pow(c, x, load_fp(b)); break;
         }
         store_fp2(out + 8 * gt_slot(c.k()), r);

@@ -173,6 +173,27 @@ def test_bilinearity_on_gpu(bn):
     assert not any(np.array_equal(x, one) for x in a)
 
 
+def test_fused_pairing_pow(bn):
+    """Joux pattern (reference examples/joux.rs:19-21): pairing(P, Q).pow(s) fused == pairing then Gt::pow == oracle."""
+    n = 27
+    g1, g2 = util.synth_pairs(0x10AD, n)
+    e1, e2 = util.edge_case_pairs()
+    g1[5:5 + len(e1)], g2[5:5 + len(e2)] = e1, e2
+    s = util.synth_scalars(0x10AE, n)
+    for i, v in enumerate([0, 1, 2, 3, o.R_ORDER - 1]):
+        s[i] = util.fr_img(v)
+    fused = bn.pairing_pow_batch(g1, g2, s)
+    assert np.array_equal(fused, bn.gt_pow_batch(bn.pairing_batch(g1, g2), s))
+    assert np.array_equal(fused, cref.gt_pow_batch(cref.pairing_batch(g1, g2, 8), s, 8))
+    # three-party key agreement: e(bP, cQ)^a == e(cP, aQ)^b == e(aP, bQ)^c
+    sk = util.synth_scalars(0x10AF, 3)
+    gen1, gen2 = cref.g1_generator(), cref.g2_generator()
+    pk1 = bn.g1_mul_batch(np.repeat(gen1, 3, axis=0), sk)
+    pk2 = bn.g2_mul_batch(np.repeat(gen2, 3, axis=0), sk)
+    ss = bn.pairing_pow_batch(pk1[[1, 2, 0]], pk2[[2, 0, 1]], sk)
+    assert np.array_equal(ss[0], ss[1]) and np.array_equal(ss[1], ss[2])
+
+
 def test_full_size_config4_properties(bn):
     """BASELINE config 4 size (2^14): the oracle cannot finish this in seconds, so check size-independent
     properties: a sampled subset is bit-exact vs the oracle, and e(P, Q)*e(-P, Q) == 1 for every pair."""

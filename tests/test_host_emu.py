@@ -154,6 +154,8 @@ def test_hexad_fq12_ops(pairs):
     assert np.array_equal(emu.gt_op(3, s), util.gt_img(o.fq12_inv(want)))
     k = o.synth_scalar(9, 0)
     assert np.array_equal(emu.gt_op(8, a, _w(k)), cref.gt_pow_batch(a[None], util.fr_img(k)[None])[0])
+    for kk in (k, 0, 1, 2, 3, o.R_ORDER - 1):  # cyclotomic fixed-window pow == generic pow on pairing values
+        assert np.array_equal(emu.gt_op(9, a, _w(kk)), cref.gt_pow_batch(a[None], util.fr_img(kk)[None])[0]), kk
 
 
 def test_pairing_kat_and_random(pairs):
