@@ -100,6 +100,17 @@ BN_HD void acck_finish(const AccK& A, Wide& a0, Wide& a1) {
 #ifndef BN_MAC_NOINLINE
 #define BN_MAC_NOINLINE 0
 #endif
+#ifndef BN_SMALL_CODE
+#define BN_SMALL_CODE 0
+#endif
+#if BN_SMALL_CODE
+// out-of-line modular add/sub for the hexad operations' glue code (instruction-cache footprint experiments)
+BN_HD_NOINLINE Fp2 fp2_add_s(Fp2 a, Fp2 b) { return fp2_add(a, b); }
+BN_HD_NOINLINE Fp2 fp2_sub_s(Fp2 a, Fp2 b) { return fp2_sub(a, b); }
+#else
+BN_HD Fp2 fp2_add_s(const Fp2& a, const Fp2& b) { return fp2_add(a, b); }
+BN_HD Fp2 fp2_sub_s(const Fp2& a, const Fp2& b) { return fp2_sub(a, b); }
+#endif
 #if BN_MAC_NOINLINE
 // one shared out-of-line copy of the multiply-accumulate
 BN_HD_NOINLINE AccK mac_fp2_call(AccK A, Fp2 x, Fp2 y) {  // by value: everything travels in registers
@@ -276,15 +287,15 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     c.put(2, r);
     c.sync();
     Fp2 tmp = c.get(nib(0x010503u, k), 2);
-    Fp2 r2 = fp2_add(r, r);
+    Fp2 r2 = fp2_add_s(r, r);
     // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*t5 on lane 1
     Fp2 xo = c.mul_xi(fp2_select(pre, tmp, r2));
-    Fp2 t_pre = fp2_sub(fp2_sub(r, tmp), xo);               // t0 / t2 / t4
+    Fp2 t_pre = fp2_sub_s(fp2_sub_s(r, tmp), xo);           // t0 / t2 / t4
     Fp2 t_im = fp2_select(k == 1, xo, r2);                   // t1 / t3 / xi*t5
     Fp2 t = fp2_select(pre, t_pre, t_im);
     // pre lanes: 3t - 2z = 2(t - z) + t ; other lanes: 3t + 2z = 2(t + z) + t   (statement order of fq12.rs:198-221)
-    Fp2 z = fp2_add(t, fp2_select(pre, fp2_neg(a), a));
-    return fp2_add(fp2_add(z, z), t);
+    Fp2 z = fp2_add_s(t, fp2_select(pre, fp2_neg(a), a));
+    return fp2_add_s(fp2_add_s(z, z), t);
 }
 
 // f^u then conjugate (reference exp_by_neg_z, src/fields/fq12.rs:97-101, 229-246).
