@@ -1,14 +1,16 @@
 // kernels.cu -- sm_100a kernels and the C ABI (include/bn_b200.h) of the batched BN254 engine.
 //
 // Kernel map:
-//   k_fq_mul_chain   K1  Fq Montgomery multiply chain (BASELINE config 2; measures the IMAD roofline)
-//   k_g1_mul/k_g2_mul K3 batched scalar multiplication, one thread per point
-//   k_pair_lines[_duo] K4a to_affine (one shared inversion) + the ate line schedule (88 lines, NAF walk of 6u+2), one
-//                        thread or one lane pair per pairing,
-//                        streamed to HBM in consumption order
-//   k_miller_fexp    K4b Miller accumulation + final exponentiation, one 6-lane hexad per pairing
-//                        (5 pairings per warp), all Fq12 state in registers
-//   k_gt_mul/k_gt_pow K5 batched Gt arithmetic on hexads
+//   k_fq_mul_chain    K1  Fq Montgomery multiply chain (BASELINE config 2); k_imad_peak calibrates the IMAD.WIDE roofline
+//   k_g1_mul/k_g2_mul K3  batched scalar multiplication, one thread per point (reference's chain: Jacobian limbs match)
+//   k_pair_lines_duo  K4a to_affine (one inversion per pair, batched per block) + the ate line schedule (88 lines, NAF
+//                         walk of 6u+2), one LANE PAIR per pairing, streamed to HBM in consumption order
+//                         (k_pair_lines: the one-thread-per-pairing form, kept for A/B via BN_B200_LINES=solo)
+//   k_miller_fexp     K4b Miller accumulation + final exponentiation, one 6-lane hexad per pairing (5 per warp); Fq12
+//                         state in registers, operands exchanged through shared-memory slots, lines prefetched by TMA
+//   k_miller_fexp_pow     same + fused Gt::pow (row f-1)
+//   k_gt_mul/k_gt_pow/k_gt_inv K5 batched Gt arithmetic on hexads
+//   k_fr_op, k_g1_normalize, k_g2_normalize   rows f-4 / f-3
 // There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include <cuda_runtime.h>
 
