@@ -144,92 +144,27 @@ BN_HD Fp2 hx_conj(const Ctx& c, const Fp2& a) {
     return fp2_select((c.k() & 1) != 0, fp2_neg(a), a);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Final-exponentiation engine: [cyclotomic square of res] then [res <- m * res], either part optional.
-// One out-of-line function with ONE inlined multiply-accumulate serves every Granger-Scott squaring and every dense
-// product of the final exponentiation, so that phase's hot code (this function + reduce2_wide + the xi multiplication)
-// stays inside the 32 KB instruction cache (ncu: `no_instruction` was the stall that punished higher occupancy).
-//
-// dense product (reference src/fields/fq12.rs:295-307): six rounds, receiver k takes m_j from j = k - s (mod 6) --
-//   the xi variant iff the pair (j, s) wraps past w^5, i.e. s > k -- and res_s from lane s.
-// Granger-Scott squaring of an element of the cyclotomic subgroup (reference src/fields/fq12.rs:178-227):
-//   Fq12 = Fq4[w]/(w^3 - s), Fq4 = Fq2[s]/(s^2 - xi), s = w^3: the three Fq4 coefficients are the lane pairs
-//   (0,3), (1,4), (2,5); each pair is squared with one Fq2 product per lane,
-//   (x + y s)^2 = [(x+y)(x + xi y) - xy - xi xy] + [2xy] s .
-// ------------------------------------------------------------------------------------------------
+// dense product.  reference src/fields/fq12.rs:295-307
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_sqr_mul(const Ctx c, Fp2 res, Fp2 m, int do_sqr, int do_mul) {
+BN_HD_NOINLINE Fp2 hx_mul(const Ctx c, Fp2 a, Fp2 b) {
     const int k = c.k();
-    const bool pre = (k & 1) == 0;  // squaring: lanes 0,2,4 form (x+y)(x+xi y); lanes 3,5,1 form x*y
-    // squaring pair assignment: lane0,3 <- (g0,g3); lane2,5 <- (g1,g4); lane4,1 <- (g2,g5)
-    const int lo = nib(0x120120u, k), hi = lo + 3;
+    c.sync();
+    c.put(0, a);
+    c.put(1, c.mul_xi(a));
+    c.put(2, b);
+    c.sync();
+    AccK acc;
+    acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int op = do_sqr ? 0 : 1; op <= do_mul; op++) {
-        c.sync();
-        if (op == 0) {
-            c.put(0, res);
-            c.put(1, c.mul_xi(res));
-        } else {
-            c.put(0, m);
-            c.put(1, c.mul_xi(m));
-            c.put(2, res);
-        }
-        c.sync();
-        AccK acc;
-        acck_init(acc);
-        const int nr = op == 0 ? 1 : 6;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int s_ = 0; s_ < nr; s_++) {
-            Fp2 x, y;
-            if (op == 0) {
-                Fp2 gx = c.get(lo, 0);
-                Fp2 gy = c.get(hi, 0);
-                Fp2 gxy = c.get(hi, 1);
-                // factors, components < 2q (mac_fp2 tolerates lazy operands for a single round)
-                x.c0 = fp_add_raw(gx.c0, fp_select(pre, gy.c0, fp_zero()));
-                x.c1 = fp_add_raw(gx.c1, fp_select(pre, gy.c1, fp_zero()));
-                y.c0 = fp_add_raw(fp_select(pre, gxy.c0, gy.c0), fp_select(pre, gx.c0, fp_zero()));
-                y.c1 = fp_add_raw(fp_select(pre, gxy.c1, gy.c1), fp_select(pre, gx.c1, fp_zero()));
-            } else {
-                x = c.get(mod6(k + 6 - s_), s_ > k ? 1 : 0);
-                y = c.get(s_, 2);
-            }
-            mac_fp2(acc, x, y);
-        }
-        Fp2 r = reduce2(acc);
-        if (op == 0) {
-            // partner product: lane0 <- lane3, lane2 <- lane5, lane4 <- lane1
-            c.put(2, r);
-            c.sync();
-            Fp2 tmp = c.get(nib(0x010503u, k), 2);
-            Fp2 r2 = fp2_add_s(r, r);
-            // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*t5 on lane 1
-            Fp2 xo = c.mul_xi(fp2_select(pre, tmp, r2));
-            Fp2 t_pre = fp2_sub_s(fp2_sub_s(r, tmp), xo);           // t0 / t2 / t4
-            Fp2 t_im = fp2_select(k == 1, xo, r2);                   // t1 / t3 / xi*t5
-            Fp2 t = fp2_select(pre, t_pre, t_im);
-            // pre lanes: 3t - 2z = 2(t - z) + t ; other lanes: 3t + 2z = 2(t + z) + t  (statement order of fq12.rs:198-221)
-            Fp2 z = fp2_add_s(t, fp2_select(pre, fp2_neg(res), res));
-            res = fp2_add_s(fp2_add_s(z, z), t);
-        } else {
-            res = r;
-        }
+    for (int s = 0; s < 6; s++) {
+        // receiver k takes a_j from j = k - s (mod 6); the pair (j, s) wraps past w^5 iff j + s >= 6  <=>  s > k
+        Fp2 x = c.get(mod6(k + 6 - s), s > k ? 1 : 0);
+        Fp2 y = c.get(s, 2);
+        mac_fp2(acc, x, y);
     }
-    return res;
-}
-// a * b
-template <class Ctx>
-BN_HD Fp2 hx_mul(const Ctx& c, const Fp2& a, const Fp2& b) {
-    return hx_sqr_mul(c, b, a, 0, 1);
-}
-// Granger-Scott square (cyclotomic subgroup only)
-template <class Ctx>
-BN_HD Fp2 hx_cyc_sqr(const Ctx& c, const Fp2& a) {
-    return hx_sqr_mul(c, a, a, 1, 0);
+    return reduce2(acc);
 }
 
 // square.  reference src/fields/fq12.rs:275-282.  21 distinct products in 4 lock-step rounds:
@@ -322,6 +257,47 @@ BN_HD Fp2 hx_frob(const Ctx& c, const Fp2& a, int p) {
     return fp2_mul(t, FROB_GAMMA_C[p - 1][c.k()]);
 }
 
+// Granger-Scott squaring of an element of the cyclotomic subgroup (reference src/fields/fq12.rs:178-227).
+// Fq12 = Fq4[w]/(w^3 - s), Fq4 = Fq2[s]/(s^2 - xi), s = w^3: the three Fq4 coefficients are the lane pairs
+// (0,3), (1,4), (2,5).  Each pair is squared with one Fq2 product per lane
+//   (x + y s)^2 = [(x+y)(x + xi y) - xy - xi xy] + [2xy] s .
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
+    const int k = c.k();
+    const bool pre = (k & 1) == 0;  // lanes 0,2,4 form (x+y)(x+xi y); lanes 3,5,1 form x*y
+    // pair assignment: lane0,3 <- (g0,g3); lane2,5 <- (g1,g4); lane4,1 <- (g2,g5)
+    const int lo = nib(0x120120u, k), hi = lo + 3;
+    c.sync();
+    c.put(0, a);
+    c.put(1, c.mul_xi(a));
+    c.sync();
+    Fp2 x = c.get(lo, 0);
+    Fp2 y = c.get(hi, 0);
+    Fp2 xy = c.get(hi, 1);
+    Fp2 f0, f1;  // factors, components < 2q
+    f0.c0 = fp_add_raw(x.c0, fp_select(pre, y.c0, fp_zero()));
+    f0.c1 = fp_add_raw(x.c1, fp_select(pre, y.c1, fp_zero()));
+    f1.c0 = fp_add_raw(fp_select(pre, xy.c0, y.c0), fp_select(pre, x.c0, fp_zero()));
+    f1.c1 = fp_add_raw(fp_select(pre, xy.c1, y.c1), fp_select(pre, x.c1, fp_zero()));
+    AccK acc;
+    acck_init(acc);
+    mac_fp2(acc, f0, f1);
+    Fp2 r = reduce2(acc);
+    // partner product: lane0 <- lane3, lane2 <- lane5, lane4 <- lane1
+    c.put(2, r);
+    c.sync();
+    Fp2 tmp = c.get(nib(0x010503u, k), 2);
+    Fp2 r2 = fp2_add_s(r, r);
+    // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*t5 on lane 1
+    Fp2 xo = c.mul_xi(fp2_select(pre, tmp, r2));
+    Fp2 t_pre = fp2_sub_s(fp2_sub_s(r, tmp), xo);           // t0 / t2 / t4
+    Fp2 t_im = fp2_select(k == 1, xo, r2);                   // t1 / t3 / xi*t5
+    Fp2 t = fp2_select(pre, t_pre, t_im);
+    // pre lanes: 3t - 2z = 2(t - z) + t ; other lanes: 3t + 2z = 2(t + z) + t   (statement order of fq12.rs:198-221)
+    Fp2 z = fp2_add_s(t, fp2_select(pre, fp2_neg(a), a));
+    return fp2_add_s(fp2_add_s(z, z), t);
+}
+
 // f^u then conjugate (reference exp_by_neg_z, src/fields/fq12.rs:97-101, 229-246).
 // VALID FOR ELEMENTS OF THE CYCLOTOMIC SUBGROUP ONLY (all three uses inside the final exponentiation are):
 // there f^-1 = conj(f), so u is walked in width-3 NAF (digits 0, +-1, +-3): 62 Granger-Scott squarings and
@@ -332,10 +308,12 @@ BN_HD_NOINLINE Fp2 hx_exp_by_neg_z(const Ctx c, Fp2 a) {
     Fp2 a3 = hx_mul(c, hx_cyc_sqr(c, a), a);
     Fp2 res = a;  // leading digit is +1
     for (int b = BN_U_WNAF_LEN - 2; b >= 0; b--) {
-        const int nz = (int)((BN_U_WNAF_NZ >> b) & 1ULL);
-        Fp2 m = ((BN_U_WNAF_3 >> b) & 1ULL) ? a3 : a;
-        if ((BN_U_WNAF_NEG >> b) & 1ULL) m = hx_conj(c, m);
-        res = hx_sqr_mul(c, res, m, 1, nz);  // res <- res^2 [* m]
+        res = hx_cyc_sqr(c, res);
+        if ((BN_U_WNAF_NZ >> b) & 1ULL) {
+            Fp2 m = ((BN_U_WNAF_3 >> b) & 1ULL) ? a3 : a;
+            if ((BN_U_WNAF_NEG >> b) & 1ULL) m = hx_conj(c, m);
+            res = hx_mul(c, m, res);
+        }
     }
     return hx_conj(c, res);
 }
