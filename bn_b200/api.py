@@ -114,6 +114,24 @@ def g2_normalize_batch(g2, device: int = 0) -> np.ndarray:
     return out
 
 
+def g1_check_batch(g1, device: int = 0) -> np.ndarray:
+    """On-curve check of decoded G1 points (reference AffineG::decode, src/groups/mod.rs:178-205) -> bool[n]."""
+    lib = _lib.init(device)
+    g1 = _arr(g1, G1_WORDS)
+    ok = np.zeros(len(g1), dtype=np.uint8)
+    _lib.check(lib.bn_b200_g1_check_batch(_p(g1), ok.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(g1))))
+    return ok.astype(bool)
+
+
+def g2_check_batch(g2, device: int = 0) -> np.ndarray:
+    """On-curve + order-r subgroup check of decoded G2 points (src/groups/mod.rs:183-195) -> bool[n]."""
+    lib = _lib.init(device)
+    g2 = _arr(g2, G2_WORDS)
+    ok = np.zeros(len(g2), dtype=np.uint8)
+    _lib.check(lib.bn_b200_g2_check_batch(_p(g2), ok.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(g2))))
+    return ok.astype(bool)
+
+
 def fq_mul_chain(a, b, iters: int, device: int = 0) -> np.ndarray:
     """x <- x*b (Montgomery mod q) `iters` times per element (BASELINE config 2)."""
     lib = _lib.init(device)

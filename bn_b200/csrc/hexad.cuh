@@ -80,7 +80,33 @@ BN_HD void acck_init(AccK& A) {
         A.a1.w[i] = 0;
     }
 }
+#ifndef BN_MAC_ROWMAJOR
+#define BN_MAC_ROWMAJOR 0
+#endif
 BN_HD void mac_fp2_inl(AccK& A, const Fp2& x, const Fp2& y) {
+#if BN_MAC_ROWMAJOR
+    // the three Karatsuba products advance row by row together: six independent IMAD.WIDE carry chains in flight
+    uint32_t E0[18], O0[16], E1[18], O1[16], E2[18], O2[16];
+    BN_UNROLL
+    for (int i = 0; i < 18; i++) E0[i] = E1[i] = E2[i] = 0;
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) O0[i] = O1[i] = O2[i] = 0;
+    const Fp sx = fp_add_raw(x.c0, x.c1), sy = fp_add_raw(y.c0, y.c1);
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) {
+        eo_row(E0, O0, x.c0.v, y.c0.v[i], i);
+        eo_row(E1, O1, x.c1.v, y.c1.v[i], i);
+        eo_row(E2, O2, sx.v, sy.v[i], i);
+    }
+    add16_shift1(E0, O0);
+    add16_shift1(E1, O1);
+    add16_shift1(E2, O2);
+    add16(A.a0.w, E0);
+    sub16(A.a1.w, E0);
+    sub16(A.a0.w, E1);
+    sub16(A.a1.w, E1);
+    add16(A.a1.w, E2);
+#else
     Wide T;
     wide_mul(T, x.c0, y.c0);
     add16(A.a0.w, T.w);
@@ -90,6 +116,7 @@ BN_HD void mac_fp2_inl(AccK& A, const Fp2& x, const Fp2& y) {
     sub16(A.a1.w, T.w);
     wide_mul(T, fp_add_raw(x.c0, x.c1), fp_add_raw(y.c0, y.c1));
     add16(A.a1.w, T.w);
+#endif
 }
 BN_HD void acck_finish(const AccK& A, Wide& a0, Wide& a1) {
     a0 = A.a0;

@@ -345,6 +345,37 @@ __global__ void __launch_bounds__(128) k_g2_normalize(const uint32_t* __restrict
     st_fp2(out + i * 48 + 32, z);
 }
 
+// Decode-side validity checks (row f-3; reference AffineG::decode, src/groups/mod.rs:178-205): the point is given as
+// (x, y, z = one) in Montgomery form (what to_jacobian() yields after Fq::new); ok = on the curve y^2 = x^3 + b and, for
+// G2 (check_order() = true, :399), in the order-r subgroup: p * (-1) + p == zero.  z = 0 (the "00" encoding) is accepted.
+__global__ void __launch_bounds__(128) k_g1_check(const uint32_t* __restrict__ p, uint8_t* __restrict__ ok, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x = ld_fp(p + i * 24), y = ld_fp(p + i * 24 + 8), z = ld_fp(p + i * 24 + 16);
+    Fp b;
+#pragma unroll
+    for (int l = 0; l < 8; l++) b.v[l] = G1_B_f(l);
+    bool good = fp_eq(fp_mul<MQ>(y, y), fp_add<MQ>(fp_mul<MQ>(fp_mul<MQ>(x, x), x), b));
+    ok[i] = (fp_is_zero(z) || good) ? 1 : 0;
+}
+__global__ void __launch_bounds__(128) k_g2_check(const uint32_t* __restrict__ p, uint8_t* __restrict__ ok, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Jac<Fq2Ops> P;
+    P.x = ld_fp2(p + i * 48);
+    P.y = ld_fp2(p + i * 48 + 16);
+    P.z = ld_fp2(p + i * 48 + 32);
+    bool good = fp2_eq(fp2_sqr(P.y), fp2_add(fp2_mul(fp2_sqr(P.x), P.x), g2_coeff_b()));
+    if (good && !fp2_is_zero(P.z)) {
+        Fp m1;
+#pragma unroll
+        for (int l = 0; l < 8; l++) m1.v[l] = FR_MINUS_ONE_f(l);
+        Jac<Fq2Ops> r = jac_add<Fq2Ops>(jac_mul<Fq2Ops>(P, m1), P);
+        good = fp2_is_zero(r.z);
+    }
+    ok[i] = (fp2_is_zero(P.z) || good) ? 1 : 0;
+}
+
 // K4a: one thread per pairing.  flags[p] = 1 when the pair is finite, 0 when either point is infinity.
 __global__ void __launch_bounds__(64) k_pair_lines(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
                                                    uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
@@ -864,6 +895,34 @@ int bn_b200_fr_op_batch(int op, const bn_fr* a, const bn_fr* b, bn_fr* out, size
                              return 0;                                                                              \
                          });                                                                                        \
     }
+#define DEFINE_CHECK(NAME, KERNEL, T)                                                                              \
+    int bn_b200_##NAME##_check_batch_dev(const T* d_p, uint8_t* d_ok, size_t n, void* stream) {                     \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
+        int rc = ensure_ready();                                                                                    \
+        if (rc) return rc;                                                                                          \
+        if (n && (!d_p || !d_ok)) return fail(BN_B200_EINVAL, "null pointer");                                      \
+        if (n == 0) return 0;                                                                                       \
+        KERNEL<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(W(d_p), d_ok, n);          \
+        g_launches += 1;                                                                                            \
+        CU(cudaGetLastError());                                                                                     \
+        return 0;                                                                                                   \
+    }                                                                                                               \
+    int bn_b200_##NAME##_check_batch(const T* p, uint8_t* ok, size_t n) {                                           \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
+        int rc = ensure_ready();                                                                                    \
+        if (rc) return rc;                                                                                          \
+        if (n == 0) return 0;                                                                                       \
+        if (!p || !ok) return fail(BN_B200_EINVAL, "null pointer");                                                 \
+        return host_call(p, n * sizeof(T), p, sizeof(T), ok, n,                                                     \
+                         [&](void* x, void*, void* o, cudaStream_t st) {                                            \
+                             KERNEL<<<blocks_for(n, 128), 128, 0, st>>>(W(x), (uint8_t*)o, n);                      \
+                             g_launches += 1;                                                                       \
+                             CU(cudaGetLastError());                                                                \
+                             return 0;                                                                              \
+                         });                                                                                        \
+    }
+DEFINE_CHECK(g1, k_g1_check, bn_g1)
+DEFINE_CHECK(g2, k_g2_check, bn_g2)
 DEFINE_NORMALIZE(g1, k_g1_normalize, bn_g1)
 DEFINE_NORMALIZE(g2, k_g2_normalize, bn_g2)
 

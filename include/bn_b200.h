@@ -92,6 +92,14 @@ int bn_b200_g1_normalize_batch_dev(const bn_g1* d_p, bn_g1* d_out, size_t n, voi
 int bn_b200_g2_normalize_batch(const bn_g2* p, bn_g2* out, size_t n);
 int bn_b200_g2_normalize_batch_dev(const bn_g2* d_p, bn_g2* d_out, size_t n, void* stream);
 
+/* Decode-side validity of n points given as (x, y, z = one) (row f-3): ok[i] = 1 iff on the curve and, for G2, in the
+ * order-r subgroup (p * (-1) + p == zero); z = 0 is accepted.  replaces the checks of AffineG::decode,
+ * src/groups/mod.rs:178-205 (the byte parsing and the `< modulus` range checks stay on the host). */
+int bn_b200_g1_check_batch(const bn_g1* p, uint8_t* ok, size_t n);
+int bn_b200_g1_check_batch_dev(const bn_g1* d_p, uint8_t* d_ok, size_t n, void* stream);
+int bn_b200_g2_check_batch(const bn_g2* p, uint8_t* ok, size_t n);
+int bn_b200_g2_check_batch_dev(const bn_g2* d_p, uint8_t* d_ok, size_t n, void* stream);
+
 /* x <- x * b (Montgomery, mod q) repeated `iters` times per element: the BASELINE config-2 microbenchmark of
  * the innermost operation (Fq Mul, src/fields/fp.rs:137-146 -> U256::mul src/arith.rs:257-263). a, b, out: n x 4 u64. */
 int bn_b200_fq_mul_chain(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, uint32_t iters);

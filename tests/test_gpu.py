@@ -138,6 +138,62 @@ def test_normalize_and_wire_vectors(bn):
     assert np.array_equal(bn.g2_normalize_batch(inf2), inf2)
 
 
+def _fq2_sqrt(a):
+    """Square root in Fq2 for q = 3 mod 4 (None if a is a non-residue); test helper for off-subgroup G2 points."""
+    if a == (0, 0):
+        return a
+    a1 = o.fq2_pow(a, (o.Q - 3) // 4)
+    alpha = o.fq2_mul(o.fq2_sqr(a1), a)
+    a0 = o.fq2_mul(o.fq2_conj(alpha), alpha)
+    if a0 == (o.Q - 1, 0):
+        return None
+    x0 = o.fq2_mul(a1, a)
+    if alpha == (o.Q - 1, 0):
+        return o.fq2_mul((0, 1), x0)
+    b = o.fq2_pow(o.fq2_add(o.FQ2_ONE, alpha), (o.Q - 1) // 2)
+    return o.fq2_mul(b, x0)
+
+
+def test_decode_checks(bn):
+    """On-curve / subgroup checks of AffineG::decode (src/groups/mod.rs:178-205) on the GPU, incl. the reference's
+    'not on the curve' edge vectors (tests/serialization.rs:66-68) and G2 points on the twist but outside the subgroup."""
+    n = 40
+    g1, g2 = util.synth_pairs(0xDEC0, n)
+    a1 = bn.g1_normalize_batch(g1)
+    a2 = bn.g2_normalize_batch(g2)
+    a1[3] = util.g1_img(o.g_zero(o.FQ))
+    a2[4] = util.g2_img(o.g_zero(o.FQ2))
+    bad1 = a1.copy()
+    bad1[:, 4] ^= np.uint64(2)  # perturb y
+    bad2 = a2.copy()
+    bad2[:, 8] ^= np.uint64(2)
+    assert bn.g1_check_batch(a1).all() and bn.g2_check_batch(a2).all()
+    r1, r2 = bn.g1_check_batch(bad1), bn.g2_check_batch(bad2)
+    assert not r1[np.arange(n) != 3].any() and r1[3]   # the zero point stays acceptable
+    assert not r2[np.arange(n) != 4].any() and r2[4]
+    # the reference's own off-curve vectors (x, y taken from the hex, bypassing the host-side decoder)
+    for kind, hx in util.load_json("wire_edge_cases.json")["cases"]:
+        b = bytes.fromhex(hx)
+        if kind == "G1" and len(b) == 65:
+            x, y = int.from_bytes(b[1:33], "big"), int.from_bytes(b[33:65], "big")
+            assert not bn.g1_check_batch(util.g1_img((x, y, 1))[None])[0]
+    # points on the twist y^2 = x^3 + 3/xi that are NOT in the order-r subgroup
+    found = 0
+    for xv in range(1, 60):
+        x = (xv, 1)
+        y = _fq2_sqrt(o.fq2_add(o.fq2_mul(o.fq2_sqr(x), x), o.G2_B))
+        if y is None:
+            continue
+        p = (x, y, o.FQ2_ONE)
+        assert o.fq2_sqr(y) == o.fq2_add(o.fq2_mul(o.fq2_sqr(x), x), o.G2_B)
+        in_subgroup = o.g_is_zero(o.FQ2, o.g_add(o.FQ2, o.g_mul(o.FQ2, p, o.R_ORDER - 1), p))
+        assert bool(bn.g2_check_batch(util.g2_img(p)[None])[0]) == in_subgroup
+        found += not in_subgroup
+        if found >= 3:
+            break
+    assert found >= 3
+
+
 def test_gt_mul_pow(bn):
     n = 23
     g1, g2 = util.synth_pairs(77, n)
