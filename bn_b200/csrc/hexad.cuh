@@ -39,74 +39,24 @@ namespace bn {
 // Montgomery reduction plus two conditional subtractions brings back to canonical form.
 // IMAD.WIDE is the scarce resource on B200 (quarter-rate), the ~170 IADD3 per step ride on the ALU pipe.
 // ------------------------------------------------------------------------------------------------
-#ifndef BN_ACC3
-#define BN_ACC3 0   // three carry-save accumulators (1) vs two merged 512-bit accumulators (0): within 1 % of each other (profiles/README.md, runs 7-10)
-#endif
-#if BN_ACC3
-// Variant: three carry-save accumulators (P0 = sum x0 y0, P1 = sum x1 y1, P2 = sum (x0+x1)(y0+y1)); the round loop is
-// then almost pure IMAD.WIDE (one IADD3.X per 4-IMAD chain) and the Karatsuba recombination happens once per
-// reduction.  Costs 120 accumulator registers.
-struct AccK {
-    AccEO p0, p1, p2;
-};
-BN_HD void acck_init(AccK& A) {
-    acc_zero(A.p0);
-    acc_zero(A.p1);
-    acc_zero(A.p2);
-}
-BN_HD void mac_fp2_inl(AccK& A, const Fp2& x, const Fp2& y) {
-    acc_mac(A.p0, x.c0, y.c0);
-    acc_mac(A.p1, x.c1, y.c1);
-    acc_mac(A.p2, fp_add_raw(x.c0, x.c1), fp_add_raw(y.c0, y.c1));
-}
-BN_HD void acck_finish(const AccK& A, Wide& a0, Wide& a1) {
-    Wide t0 = acc_merge(A.p0), t1 = acc_merge(A.p1);
-    a1 = acc_merge(A.p2);
-    sub16(a1.w, t0.w);
-    sub16(a1.w, t1.w);
-    BN_UNROLL
-    for (int i = 0; i < 16; i++) a0.w[i] = WIDE_6Q2_f(i);
-    add16(a0.w, t0.w);
-    sub16(a0.w, t1.w);
-}
-#else
-struct AccK {
+// Two accumulator layouts (both measured, profiles/README.md):
+//   AccK2  two merged 512-bit accumulators; every product is merged and added/subtracted as it is produced
+//          (~190 IADD3 per round, 32 accumulator registers)
+//   AccK3  three carry-save accumulators P0 = sum x0 y0, P1 = sum x1 y1, P2 = sum (x0+x1)(y0+y1); the round loop is
+//          almost pure IMAD.WIDE (one IADD3.X per 4-IMAD chain) and the Karatsuba recombination happens once per
+//          reduction (~64 IADD3 per round + ~160 per operation, 120 accumulator registers)
+// The choice is made per operation (BN_ACC_MUL / _SQR / _LINE / _CYC = 2 or 3).
+struct AccK2 {
     Wide a0, a1;
 };
-BN_HD void acck_init(AccK& A) {
+BN_HD void acck_init(AccK2& A) {
     BN_UNROLL
     for (int i = 0; i < 16; i++) {
         A.a0.w[i] = WIDE_6Q2_f(i);
         A.a1.w[i] = 0;
     }
 }
-#ifndef BN_MAC_ROWMAJOR
-#define BN_MAC_ROWMAJOR 0
-#endif
-BN_HD void mac_fp2_inl(AccK& A, const Fp2& x, const Fp2& y) {
-#if BN_MAC_ROWMAJOR
-    // the three Karatsuba products advance row by row together: six independent IMAD.WIDE carry chains in flight
-    uint32_t E0[18], O0[16], E1[18], O1[16], E2[18], O2[16];
-    BN_UNROLL
-    for (int i = 0; i < 18; i++) E0[i] = E1[i] = E2[i] = 0;
-    BN_UNROLL
-    for (int i = 0; i < 16; i++) O0[i] = O1[i] = O2[i] = 0;
-    const Fp sx = fp_add_raw(x.c0, x.c1), sy = fp_add_raw(y.c0, y.c1);
-    BN_UNROLL
-    for (int i = 0; i < 8; i++) {
-        eo_row(E0, O0, x.c0.v, y.c0.v[i], i);
-        eo_row(E1, O1, x.c1.v, y.c1.v[i], i);
-        eo_row(E2, O2, sx.v, sy.v[i], i);
-    }
-    add16_shift1(E0, O0);
-    add16_shift1(E1, O1);
-    add16_shift1(E2, O2);
-    add16(A.a0.w, E0);
-    sub16(A.a1.w, E0);
-    sub16(A.a0.w, E1);
-    sub16(A.a1.w, E1);
-    add16(A.a1.w, E2);
-#else
+BN_HD void mac_fp2(AccK2& A, const Fp2& x, const Fp2& y) {
     Wide T;
     wide_mul(T, x.c0, y.c0);
     add16(A.a0.w, T.w);
@@ -116,17 +66,55 @@ BN_HD void mac_fp2_inl(AccK& A, const Fp2& x, const Fp2& y) {
     sub16(A.a1.w, T.w);
     wide_mul(T, fp_add_raw(x.c0, x.c1), fp_add_raw(y.c0, y.c1));
     add16(A.a1.w, T.w);
-#endif
 }
-BN_HD void acck_finish(const AccK& A, Wide& a0, Wide& a1) {
+BN_HD void acck_finish(const AccK2& A, Wide& a0, Wide& a1) {
     a0 = A.a0;
     a1 = A.a1;
 }
+struct AccK3 {
+    AccEO p0, p1, p2;
+};
+BN_HD void acck_init(AccK3& A) {
+    acc_zero(A.p0);
+    acc_zero(A.p1);
+    acc_zero(A.p2);
+}
+BN_HD void mac_fp2(AccK3& A, const Fp2& x, const Fp2& y) {
+    acc_mac(A.p0, x.c0, y.c0);
+    acc_mac(A.p1, x.c1, y.c1);
+    acc_mac(A.p2, fp_add_raw(x.c0, x.c1), fp_add_raw(y.c0, y.c1));
+}
+BN_HD void acck_finish(const AccK3& A, Wide& a0, Wide& a1) {
+    Wide t0 = acc_merge(A.p0), t1 = acc_merge(A.p1);
+    a1 = acc_merge(A.p2);
+    sub16(a1.w, t0.w);
+    sub16(a1.w, t1.w);
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) a0.w[i] = WIDE_6Q2_f(i);
+    add16(a0.w, t0.w);
+    sub16(a0.w, t1.w);
+}
+template <int N>
+struct AccSel {
+    typedef AccK2 type;
+};
+template <>
+struct AccSel<3> {
+    typedef AccK3 type;
+};
+#ifndef BN_ACC_MUL
+#define BN_ACC_MUL 2
 #endif
-// one shared copy of the two Montgomery reductions (code footprint: the hot loop must stay inside the 32 KB I-cache)
-#ifndef BN_MAC_NOINLINE
-#define BN_MAC_NOINLINE 0
+#ifndef BN_ACC_SQR
+#define BN_ACC_SQR 2
 #endif
+#ifndef BN_ACC_LINE
+#define BN_ACC_LINE 3   // run 22: 6.84 ms vs 6.93 ms; the same change on the dense product or the squaring loses (7.10-7.12 ms)
+#endif
+#ifndef BN_ACC_CYC
+#define BN_ACC_CYC 2
+#endif
+
 #ifndef BN_SMALL_CODE
 #define BN_SMALL_CODE 0
 #endif
@@ -138,23 +126,14 @@ BN_HD_NOINLINE Fp2 fp2_sub_s(Fp2 a, Fp2 b) { return fp2_sub(a, b); }
 BN_HD Fp2 fp2_add_s(const Fp2& a, const Fp2& b) { return fp2_add(a, b); }
 BN_HD Fp2 fp2_sub_s(const Fp2& a, const Fp2& b) { return fp2_sub(a, b); }
 #endif
-#if BN_MAC_NOINLINE
-// one shared out-of-line copy of the multiply-accumulate
-BN_HD_NOINLINE AccK mac_fp2_call(AccK A, Fp2 x, Fp2 y) {  // by value: everything travels in registers
-    mac_fp2_inl(A, x, y);
-    return A;
-}
-BN_HD void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) { A = mac_fp2_call(A, x, y); }
-#else
-BN_HD void mac_fp2(AccK& A, const Fp2& x, const Fp2& y) { mac_fp2_inl(A, x, y); }
-#endif
+// one shared copy of the two Montgomery reductions (code footprint: the hot loops must stay inside the 32 KB I-cache)
 BN_HD_NOINLINE Fp2 reduce2_wide(Wide a0, Wide a1) { return Fp2{mont_reduce<MQ, 4>(a0), mont_reduce<MQ, 4>(a1)}; }
-BN_HD Fp2 reduce2(const AccK& A) {
+template <class ACC>
+BN_HD Fp2 reduce2(const ACC& A) {
     Wide a0, a1;
     acck_finish(A, a0, a1);
     return reduce2_wide(a0, a1);
 }
-
 
 BN_HD int nib(uint32_t packed, int k) { return (int)((packed >> (4 * k)) & 7u); }
 BN_HD int mod6(int x) { return x >= 6 ? x - 6 : x; }
@@ -180,7 +159,7 @@ BN_HD_NOINLINE Fp2 hx_mul(const Ctx c, Fp2 a, Fp2 b) {
     c.put(1, c.mul_xi(a));
     c.put(2, b);
     c.sync();
-    AccK acc;
+    typename AccSel<BN_ACC_MUL>::type acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -209,7 +188,7 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
         c.put(2, fp2_dbl(fp2_select(k >= 4, xa, a)));  // doubled operand: 2 a_k on lanes 0..3, 2 xi a_k on lanes 4,5
         c.sync();
     }
-    AccK acc;
+    typename AccSel<BN_ACC_SQR>::type acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -241,7 +220,7 @@ BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, Fp2 l0, Fp2 l3k, Fp2 l4k) {
     c.sync();
     c.put(0, a);
     c.sync();
-    AccK acc;
+    typename AccSel<BN_ACC_LINE>::type acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -263,7 +242,7 @@ BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx c, Fp2 a, Fp2 m0, Fp2 m1, Fp2 m2) {
     c.sync();
     c.put(0, a);
     c.sync();
-    AccK acc;
+    typename AccSel<BN_ACC_LINE>::type acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -306,7 +285,7 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     f0.c1 = fp_add_raw(x.c1, fp_select(pre, y.c1, fp_zero()));
     f1.c0 = fp_add_raw(fp_select(pre, xy.c0, y.c0), fp_select(pre, x.c0, fp_zero()));
     f1.c1 = fp_add_raw(fp_select(pre, xy.c1, y.c1), fp_select(pre, x.c1, fp_zero()));
-    AccK acc;
+    typename AccSel<BN_ACC_CYC>::type acc;
     acck_init(acc);
     mac_fp2(acc, f0, f1);
     Fp2 r = reduce2(acc);
