@@ -118,6 +118,14 @@ struct AccSel<3> {
 #ifndef BN_SMALL_CODE
 #define BN_SMALL_CODE 0
 #endif
+#define BN_PRAGMA_(x) _Pragma(#x)
+#define BN_UNROLL_N(n) BN_PRAGMA_(unroll n)
+#ifndef BN_MUL_UNROLL
+#define BN_MUL_UNROLL 1   // unroll factor of the six-round dense-product loop
+#endif
+#ifndef BN_SQR_UNROLL
+#define BN_SQR_UNROLL 1
+#endif
 #if BN_SMALL_CODE
 // out-of-line modular add/sub for the hexad operations' glue code (instruction-cache footprint experiments)
 BN_HD_NOINLINE Fp2 fp2_add_s(Fp2 a, Fp2 b) { return fp2_add(a, b); }
@@ -162,7 +170,7 @@ BN_HD_NOINLINE Fp2 hx_mul(const Ctx c, Fp2 a, Fp2 b) {
     typename AccSel<BN_ACC_MUL>::type acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+BN_UNROLL_N(BN_MUL_UNROLL)
 #endif
     for (int s = 0; s < 6; s++) {
         // receiver k takes a_j from j = k - s (mod 6); the pair (j, s) wraps past w^5 iff j + s >= 6  <=>  s > k
@@ -191,7 +199,7 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
     typename AccSel<BN_ACC_SQR>::type acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+BN_UNROLL_N(BN_SQR_UNROLL)
 #endif
     for (int r = 0; r < 4; r++) {
         // x sources / y sources per lane (nibble k), per round:

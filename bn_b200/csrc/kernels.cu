@@ -429,7 +429,10 @@ struct DevDuoLineSink {
         }
     }
 };
-__global__ void __launch_bounds__(64) k_pair_lines_duo(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
+#ifndef DUO_BLOCK
+#define DUO_BLOCK 32   // threads per block (run 23: 32 -> 1.589 ms, 64 -> 1.613 ms, 128 -> 1.614 ms); of the lane-pair line kernel (DUO_BLOCK/2 pairings share one batched inversion)
+#endif
+__global__ void __launch_bounds__(DUO_BLOCK) k_pair_lines_duo(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
                                                        uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t i = t >> 1;
@@ -446,9 +449,9 @@ __global__ void __launch_bounds__(64) k_pair_lines_duo(const uint32_t* __restric
     DuoX<DevDuo> X_{DevDuo{(int)(t & 1)}};
     Fp px, py;
     Fp2 qx, qy;
-    __shared__ Fp s_val[32], s_pre[32];  // 64 threads = 32 pairings per block
+    __shared__ Fp s_val[DUO_BLOCK / 2], s_pre[DUO_BLOCK / 2];  // one slot per pairing of the block
     const int slot = (int)(threadIdx.x >> 1);
-    auto inv = [&](const Fp& x) { return block_batch_inv(x, (threadIdx.x & 1) == 0 ? slot : -1, slot, 32, s_val, s_pre); };
+    auto inv = [&](const Fp& x) { return block_batch_inv(x, (threadIdx.x & 1) == 0 ? slot : -1, slot, DUO_BLOCK / 2, s_val, s_pre); };
     bool finite = pair_to_affine(X_, inv, P, Q, px, py, qx, qy);
     if (active && (t & 1) == 0) flags[i] = finite ? 1 : 0;
     DevDuoLineSink sink{lines, n, i, (int)(t & 1), active};
@@ -627,7 +630,7 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_
     if (rc) return rc;
     if (g.profiling) CU(cudaEventRecord(g.ev[0], st));
     if (g.lines_duo)
-        k_pair_lines_duo<<<blocks_for(2 * n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
+        k_pair_lines_duo<<<blocks_for(2 * n, DUO_BLOCK), DUO_BLOCK, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
     else
         k_pair_lines<<<blocks_for(n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
     if (g.profiling) CU(cudaEventRecord(g.ev[1], st));
