@@ -65,7 +65,7 @@ BN_HD_NOINLINE Fp2 duo_mul_xi(const D d, Fp2 a) {
     c = addi8(v, addend.v);
     v[8] += c;
     Fp r;
-    fp_small_reduce9(v, r.v, nullptr);
+    fp_small_reduce9(v, r.v, KqNone());
     return duo_join(d, r);
 }
 

@@ -169,21 +169,30 @@ BN_HD void kq_table_fill(uint32_t* tab, int k) {  // fill row k (callers split r
 
 // v (9 limbs, < 16q) -> v mod q.  Quotient estimate from the top bits: h = floor(v / 2^251), qhat = floor(h*42/256)
 // satisfies floor(v/q) - 1 <= qhat <= floor(v/q) for v < 16q (q / 2^251 = 6.0477..., 256/42 = 6.095...), so
-// v - qhat*q lies in [0, 2q) and one conditional subtraction finishes.  tab == nullptr: binary search fallback.
-BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out, const uint32_t* tab) {
-    if (tab) {
-        const uint32_t h = (v[8] << 5) | (v[7] >> 27);
-        const uint32_t qhat = (h * 42u) >> 8;
-        const uint32_t* row = tab + qhat * BN_KQ_STRIDE;
-        uint32_t kq[8], t[8];
+// v - qhat*q lies in [0, 2q) and one conditional subtraction finishes.  `row(qhat, kq)` fetches the eight low limbs of
+// qhat*q (KqRowPtr: plain pointer, host emulation; KqRowLds in kernels.cu: ld.shared.v4 from a 32-bit shared address).
+struct KqRowPtr {
+    const uint32_t* tab;
+    BN_HD void operator()(uint32_t qhat, uint32_t* kq) const {
+        const uint32_t* r = tab + qhat * BN_KQ_STRIDE;
         BN_UNROLL
-        for (int i = 0; i < 8; i++) kq[i] = row[i];
-        (void)sub8(t, v, kq);  // the ninth limb of the difference is zero (value < 2q < 2^255)
-        cond_sub_p<MQ>(t);
-        BN_UNROLL
-        for (int i = 0; i < 8; i++) out[i] = t[i];
-        return;
+        for (int i = 0; i < 8; i++) kq[i] = r[i];
     }
+};
+template <class Row>
+BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out, const Row& row) {
+    const uint32_t h = (v[8] << 5) | (v[7] >> 27);
+    const uint32_t qhat = (h * 42u) >> 8;
+    uint32_t kq[8], t[8];
+    row(qhat, kq);
+    (void)sub8(t, v, kq);  // the ninth limb of the difference is zero (value < 2q < 2^255)
+    cond_sub_p<MQ>(t);
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) out[i] = t[i];
+}
+// table-free variant (thread-per-element kernels): binary search over 8q, 4q, 2q, q
+struct KqNone {};
+BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out, const KqNone&) {
     BN_UNROLL
     for (int sh = 3; sh >= 0; sh--) {
         uint32_t kq[9], t[9];
@@ -205,7 +214,8 @@ BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out, const uint32_t* tab) {
 }
 
 // multiply by xi = 9 + i:  (9x - y) + (9y + x) i.   reference src/fields/fq2.rs:70-72 (a full Fq2 mul there)
-BN_HD Fp2 fp2_mul_xi_tab(const Fp2& a, const uint32_t* tab) {
+template <class Row>
+BN_HD Fp2 fp2_mul_xi_tab(const Fp2& a, const Row& row) {
     Fp2 r;
     // component 0: 9*a0 + (q - a1)  in (0, 10q];  component 1: 9*a1 + a0 in [0, 10q)
     BN_UNROLL
@@ -222,13 +232,15 @@ BN_HD Fp2 fp2_mul_xi_tab(const Fp2& a, const uint32_t* tab) {
         v[8] += c;
         c = addi8(v, addend.v);
         v[8] += c;
-        fp_small_reduce9(v, comp == 0 ? r.c0.v : r.c1.v, tab);
+        fp_small_reduce9(v, comp == 0 ? r.c0.v : r.c1.v, row);
     }
     return r;
 }
-BN_HD_NOINLINE Fp2 fp2_mul_xi(Fp2 a) { return fp2_mul_xi_tab(a, nullptr); }
-// hexad kernels: reduction rows come from a k*q table in shared memory
-BN_HD_NOINLINE Fp2 fp2_mul_xi_t(Fp2 a, const uint32_t* tab) { return fp2_mul_xi_tab(a, tab); }
+BN_HD_NOINLINE Fp2 fp2_mul_xi(Fp2 a) { return fp2_mul_xi_tab(a, KqNone()); }
+// hexad kernels: reduction rows come from a k*q table (shared memory on the device)
+template <class Row>
+BN_HD_NOINLINE Fp2 fp2_mul_xi_r(Fp2 a, Row row) { return fp2_mul_xi_tab(a, row); }
+BN_HD Fp2 fp2_mul_xi_t(const Fp2& a, const uint32_t* tab) { return fp2_mul_xi_r(a, KqRowPtr{tab}); }
 
 // 1/a.   reference src/fields/fq2.rs:125-136.  a != 0.
 BN_HD Fp2 fp2_inv(const Fp2& a) {

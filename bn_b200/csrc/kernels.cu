@@ -106,32 +106,50 @@ __device__ __noinline__ Fp block_batch_inv(const Fp& x, int wslot, int rslot, in
     return val[rslot >= 0 ? rslot : 0];
 }
 
+// Shared-memory access by 32-bit shared-window address (LDS.128 / STS.128): no generic-pointer arithmetic or address
+// translation in the hexad round loops.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t* v) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+__device__ __forceinline__ Fp2 lds_fp2(uint32_t addr) {
+    Fp2 r;
+    lds128(addr, r.c0.v);
+    lds128(addr + 16, r.c0.v + 4);
+    lds128(addr + 32, r.c1.v);
+    lds128(addr + 48, r.c1.v + 4);
+    return r;
+}
+__device__ __forceinline__ void sts_fp2(uint32_t addr, const Fp2& v) {
+    sts128(addr, v.c0.v);
+    sts128(addr + 16, v.c0.v + 4);
+    sts128(addr + 32, v.c1.v);
+    sts128(addr + 48, v.c1.v + 4);
+}
+struct KqRowLds {  // row qhat of the k*q table (fp2.cuh: fp_small_reduce9)
+    uint32_t base;
+    __device__ __forceinline__ void operator()(uint32_t qhat, uint32_t* kq) const {
+        const uint32_t a = base + qhat * (BN_KQ_STRIDE * 4);
+        lds128(a, kq);
+        lds128(a + 16, kq + 4);
+    }
+};
+
 struct DevCtx {
     int kk;
     int slot;          // hexad index inside the block, or -1 for the two spare lanes of a warp
     HexSmem* sm;
-    uint32_t* mine;    // this lane's exchange slots
-    uint32_t* hexbase; // lane 0 of this hexad
+    uint32_t mine;     // shared address of this lane's exchange slots
+    uint32_t hexbase;  // shared address of lane 0 of this hexad
+    uint32_t kq;       // shared address of the k*q table
     __device__ __forceinline__ int k() const { return kk; }
-    __device__ __forceinline__ Fp2 mul_xi(const Fp2& a) const { return fp2_mul_xi_t(a, sm->kq); }
+    __device__ __forceinline__ Fp2 mul_xi(const Fp2& a) const { return fp2_mul_xi_r(a, KqRowLds{kq}); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
-    __device__ __forceinline__ void put(int s, const Fp2& v) const {
-        uint4* p = reinterpret_cast<uint4*>(mine + s * 16);
-        p[0] = make_uint4(v.c0.v[0], v.c0.v[1], v.c0.v[2], v.c0.v[3]);
-        p[1] = make_uint4(v.c0.v[4], v.c0.v[5], v.c0.v[6], v.c0.v[7]);
-        p[2] = make_uint4(v.c1.v[0], v.c1.v[1], v.c1.v[2], v.c1.v[3]);
-        p[3] = make_uint4(v.c1.v[4], v.c1.v[5], v.c1.v[6], v.c1.v[7]);
-    }
-    __device__ __forceinline__ Fp2 get(int src, int s) const {
-        const uint4* p = reinterpret_cast<const uint4*>(hexbase + src * HEX_LANE_STRIDE + s * 16);
-        const uint4 a = p[0], b = p[1], c = p[2], d = p[3];
-        Fp2 r;
-        r.c0.v[0] = a.x; r.c0.v[1] = a.y; r.c0.v[2] = a.z; r.c0.v[3] = a.w;
-        r.c0.v[4] = b.x; r.c0.v[5] = b.y; r.c0.v[6] = b.z; r.c0.v[7] = b.w;
-        r.c1.v[0] = c.x; r.c1.v[1] = c.y; r.c1.v[2] = c.z; r.c1.v[3] = c.w;
-        r.c1.v[4] = d.x; r.c1.v[5] = d.y; r.c1.v[6] = d.z; r.c1.v[7] = d.w;
-        return r;
-    }
+    __device__ __forceinline__ void put(int s, const Fp2& v) const { sts_fp2(mine + s * 64, v); }
+    __device__ __forceinline__ Fp2 get(int src, int s) const { return lds_fp2(hexbase + src * (HEX_LANE_STRIDE * 4) + s * 64); }
     __device__ __forceinline__ Fp inv(const Fp& x) const {
 #if HEX_BATCH_INV
         return block_batch_inv(x, kk == 0 ? slot : -1, slot, HEX_PER_BLOCK, sm->val, sm->pre);
@@ -156,17 +174,18 @@ struct DevLineSrc {
 // Line source fed by the TMA engine: one elected lane per warp issues a 1600-byte cp.async.bulk for Miller step t+2
 // as soon as the warp has consumed step t; completion is tracked by an mbarrier transaction count, consumers spin on
 // mbarrier.try_wait.parity (bounded, then trap: a protocol bug must fail the launch, not hang the GPU).
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 struct DevLineSrcTma {
     const uint32_t* gbase;  // lines + p0 * 80 words (row 0 of this warp's five pairings)
     size_t row_words;       // n * 80
-    LineRing* ring;
-    int hexc;               // hexad index clamped to 0..4
+    uint32_t ring;          // shared address of this warp's LineRing (buf[0], buf[1], bar[0], bar[1])
+    uint32_t lane_off;      // byte offset of this lane's hexad inside a ring buffer
     int lane;
+    __device__ __forceinline__ uint32_t bar(int b) const { return ring + 2 * HEX_LINE_BYTES + 8 * b; }
+    __device__ __forceinline__ uint32_t buf(int b) const { return ring + b * HEX_LINE_BYTES; }
     __device__ __forceinline__ void init() const {
         if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring->bar[0])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring->bar[1])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar(0)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar(1)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -175,41 +194,28 @@ struct DevLineSrcTma {
     }
     __device__ __forceinline__ void issue(int t) const {
         if (lane == 0) {
-            const uint32_t bar = smem_u32(&ring->bar[t & 1]);
-            const uint32_t dst = smem_u32(&ring->buf[t & 1][0]);
             const uint32_t* src = gbase + (size_t)t * row_words;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)HEX_LINE_BYTES) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "l"(src), "r"((uint32_t)HEX_LINE_BYTES), "r"(bar)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar(t & 1)), "r"((uint32_t)HEX_LINE_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf(t & 1)),
+                         "l"(src), "r"((uint32_t)HEX_LINE_BYTES), "r"(bar(t & 1))
                          : "memory");
         }
     }
     __device__ __forceinline__ void get(int t, int k, Fp2& l0, Fp2& l3k, Fp2& l4k) const {
-        const uint32_t bar = smem_u32(&ring->bar[t & 1]);
         const uint32_t parity = (uint32_t)(t >> 1) & 1u;
         uint32_t ok = 0;
         for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                          : "=r"(ok)
-                         : "r"(bar), "r"(parity)
+                         : "r"(bar(t & 1)), "r"(parity)
                          : "memory");
         }
         if (!ok) __trap();
-        const uint32_t* L = &ring->buf[t & 1][hexc * BN_LINE_WORDS];
-        auto lds2 = [](const uint32_t* p) {
-            const uint4* q = reinterpret_cast<const uint4*>(p);
-            const uint4 a = q[0], b = q[1], c = q[2], d = q[3];
-            Fp2 r;
-            r.c0.v[0] = a.x; r.c0.v[1] = a.y; r.c0.v[2] = a.z; r.c0.v[3] = a.w;
-            r.c0.v[4] = b.x; r.c0.v[5] = b.y; r.c0.v[6] = b.z; r.c0.v[7] = b.w;
-            r.c1.v[0] = c.x; r.c1.v[1] = c.y; r.c1.v[2] = c.z; r.c1.v[3] = c.w;
-            r.c1.v[4] = d.x; r.c1.v[5] = d.y; r.c1.v[6] = d.z; r.c1.v[7] = d.w;
-            return r;
-        };
-        l0 = lds2(L + BN_LINE_OFF_L0);
-        l3k = lds2(L + (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3));
-        l4k = lds2(L + (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4));
+        const uint32_t L = buf(t & 1) + lane_off;
+        l0 = lds_fp2(L + 4 * BN_LINE_OFF_L0);
+        l3k = lds_fp2(L + 4 * (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3));
+        l4k = lds_fp2(L + 4 * (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4));
         __syncwarp();  // every lane has read buffer t&1 -> it can be refilled
         if (t + 2 < BN_NUM_LINES) issue(t + 2);
     }
@@ -477,9 +483,10 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     h.ctx.kk = lane - hex * 6;
     h.ctx.slot = hex < HEX_PER_WARP ? warp * HEX_PER_WARP + hex : -1;
     h.ctx.sm = sm;
-    h.ctx.mine = sm->xch[warp] + lane * HEX_LANE_STRIDE;
+    h.ctx.mine = smem_u32(sm->xch[warp] + lane * HEX_LANE_STRIDE);
     // the two spare lanes (30, 31) write their own slots but read hexad 4's, so every read stays inside the warp's area
-    h.ctx.hexbase = sm->xch[warp] + (hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * 6 * HEX_LANE_STRIDE;
+    h.ctx.hexbase = smem_u32(sm->xch[warp] + (hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * 6 * HEX_LANE_STRIDE);
+    h.ctx.kq = smem_u32(sm->kq);
     size_t idx = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP + hex;
     h.active = (hex < HEX_PER_WARP) && (idx < n);
     h.pidx = h.active ? idx : (n - 1);
@@ -498,8 +505,8 @@ __device__ __forceinline__ void miller_fexp_body(const uint32_t* __restrict__ li
     size_t p0 = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP;
     if (p0 >= n) p0 = n >= HEX_PER_WARP ? n - HEX_PER_WARP : 0;  // warp with no real pairing: any valid rows will do
     const int hex = lane / 6;
-    DevLineSrcTma src{lines + p0 * BN_LINE_WORDS, n * (size_t)BN_LINE_WORDS, &smem.ring[warp],
-                      hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1, lane};
+    DevLineSrcTma src{lines + p0 * BN_LINE_WORDS, n * (size_t)BN_LINE_WORDS, smem_u32(&smem.ring[warp]),
+                      (uint32_t)((hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * BN_LINE_WORDS * 4), lane};
     src.init();
 #else
     DevLineSrc src{lines, n, h.pidx};
