@@ -46,11 +46,22 @@ namespace bn {
 // ------------------------------------------------------------------------------------------------
 // Carry-chain primitives
 // ------------------------------------------------------------------------------------------------
+// BN_MAD_VOLATILE=1 pins the multiply chains in program order (asm volatile): one dependent IMAD.WIDE.X chain already
+// issues at the fma-heavy pipe's rate (4 cycles per warp instruction), so interleaving chains buys nothing and costs
+// ptxas predicate spills (LOP3 into a mask register) and register moves.
+#ifndef BN_MAD_VOLATILE
+#define BN_MAD_VOLATILE 0
+#endif
+#if BN_MAD_VOLATILE
+#define BN_MAD_ASM asm volatile
+#else
+#define BN_MAD_ASM asm
+#endif
 
 // acc[0..7] += {x0,x1,x2,x3} * y laid out as four (lo,hi) pairs; carry-out added into acc[8].
 BN_HD void mad_row4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
 #if defined(__CUDA_ARCH__)
-    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+    BN_MAD_ASM("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
         "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
         "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
         "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
@@ -80,7 +91,7 @@ BN_HD void mad_row4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32
 // Same, without a carry-out limb (caller proved the carry is zero).
 BN_HD void mad_row4_nc(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
 #if defined(__CUDA_ARCH__)
-    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+    BN_MAD_ASM("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
         "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
         "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
         "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
@@ -582,7 +593,7 @@ BN_HD void acc_zero(AccEO& a) {
 // chain with the carry-out going to a separate counter register
 BN_HD void mad_row4_cs(uint32_t* acc, uint32_t& counter, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
 #if defined(__CUDA_ARCH__)
-    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+    BN_MAD_ASM("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
         "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
         "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
         "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"

@@ -22,7 +22,8 @@
 // 512-bit accumulators are live.
 //
 // All functions are collective over the hexad: every lane calls them with its own coefficient.
-// `Ctx` supplies k(), put(slot, value), get(source lane index within the hexad, slot), sync(), mul_xi(Fq2) and
+// `Ctx` supplies k(), put(slot, value), get(source lane index within the hexad, slot), sync(), mul_xi(Fq2),
+// park(slot, value) / unpark(slot) (lane-private storage outside the register file) and
 // inv(Fq element, identical in the six lanes); kernels.cu binds them to shared memory + __syncwarp and a block-wide batched
 // inversion, tests/host_emu binds them to a barrier exchange between six host threads and a Fermat inversion.
 #pragma once
@@ -126,6 +127,9 @@ struct AccSel<3> {
 #ifndef BN_SQR_UNROLL
 #define BN_SQR_UNROLL 1
 #endif
+#ifndef BN_LINE_UNROLL
+#define BN_LINE_UNROLL 1
+#endif
 #if BN_SMALL_CODE
 // out-of-line modular add/sub for the hexad operations' glue code (instruction-cache footprint experiments)
 BN_HD_NOINLINE Fp2 fp2_add_s(Fp2 a, Fp2 b) { return fp2_add(a, b); }
@@ -221,9 +225,11 @@ BN_UNROLL_N(BN_SQR_UNROLL)
 }
 
 // product with the sparse line l0 + l3 w^3 + l4 w^4 (reference mul_by_024, src/fields/fq12.rs:107-176).
-// l3k / l4k are ALREADY the variant this lane needs:  l3k = (k < 3 ? xi*l3 : l3), l4k = (k < 4 ? xi*l4 : l4).
-template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, Fp2 l0, Fp2 l3k, Fp2 l4k) {
+// The coefficients are read round by round from the line source (src.coef(h, 0/1/2) = l0, l3k, l4k, where l3k / l4k are
+// ALREADY the variant this lane needs:  l3k = (k < 3 ? xi*l3 : l3), l4k = (k < 4 ? xi*l4 : l4)): on the device they sit
+// in the TMA ring in shared memory, so they never occupy registers next to the 512-bit accumulators.
+template <class Ctx, class LineSrc>
+BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, const LineSrc src, typename LineSrc::Handle h) {
     const int k = c.k();
     c.sync();
     c.put(0, a);
@@ -231,11 +237,11 @@ BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, Fp2 l0, Fp2 l3k, Fp2 l4k) {
     typename AccSel<BN_ACC_LINE>::type acc;
     acck_init(acc);
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+BN_UNROLL_N(BN_LINE_UNROLL)
 #endif
     for (int r = 0; r < 3; r++) {
         Fp2 x = c.get(mod6(k + (r == 0 ? 0 : r == 1 ? 3 : 2)), 0);  // a_k, a_{k-3}, a_{k-4}
-        Fp2 y = fp2_select(r == 0, l0, fp2_select(r == 1, l3k, l4k));
+        Fp2 y = src.coef(h, r);
         mac_fp2(acc, x, y);
     }
     return reduce2(acc);
@@ -317,14 +323,23 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
 // there f^-1 = conj(f), so u is walked in width-3 NAF (digits 0, +-1, +-3): 62 Granger-Scott squarings and
 // 17 + 1 multiplications instead of the reference's 62 + 27.  Gt is canonical, so any addition chain for the same
 // exponent gives the same bytes.
+// Register diet: a and a^3 are only touched on the 18 non-zero digits, so they are PARKED in the lane's private
+// shared-memory slots (c.park / c.unpark, slots HX_PARK_A / HX_PARK_A3) and only the running value stays in registers.
+// On return slot HX_PARK_A still holds a (hx_final_exp re-reads it).
+#define HX_PARK_A 0
+#define HX_PARK_A3 1
+#define HX_PARK_X 2   // two slots for the caller's values that are idle during an exponentiation
+#define HX_PARK_Y 3
+#define HX_PARK_SLOTS 4
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_exp_by_neg_z(const Ctx c, Fp2 a) {
-    Fp2 a3 = hx_mul(c, hx_cyc_sqr(c, a), a);
-    Fp2 res = a;  // leading digit is +1
+    c.park(HX_PARK_A, a);
+    c.park(HX_PARK_A3, hx_mul(c, hx_cyc_sqr(c, a), a));
+    Fp2 res = c.unpark(HX_PARK_A);  // leading digit is +1
     for (int b = BN_U_WNAF_LEN - 2; b >= 0; b--) {
         res = hx_cyc_sqr(c, res);
         if ((BN_U_WNAF_NZ >> b) & 1ULL) {
-            Fp2 m = ((BN_U_WNAF_3 >> b) & 1ULL) ? a3 : a;
+            Fp2 m = c.unpark(((BN_U_WNAF_3 >> b) & 1ULL) ? HX_PARK_A3 : HX_PARK_A);
             if ((BN_U_WNAF_NEG >> b) & 1ULL) m = hx_conj(c, m);
             res = hx_mul(c, m, res);
         }
@@ -357,8 +372,14 @@ BN_HD_NOINLINE Fp2 hx_inv(const Ctx c, Fp2 f) {
     return hx_mul_fq6(c, fc, fp2_mul(di, t0), fp2_mul(di, t1), fp2_mul(di, t2));
 }
 
-// reference final_exponentiation, src/fields/fq12.rs:41-88 (same operation chain, hence the same exponent
-// (q^6-1)(q^2+1) * 2u(6u^2+3u+1)(q^4-q^2+1)/r that the crate's Gt values carry).
+// reference final_exponentiation, src/fields/fq12.rs:41-88: same first chunk, and a last chunk that reaches the same
+// exponent (q^6-1)(q^2+1) * 2u(6u^2+3u+1)(q^4-q^2+1)/r the crate's Gt values carry, regrouped
+// so that at most two values are idle during each exponentiation by u (they are parked in shared memory; with the
+// reference's grouping four Fq12 values = 64 registers per lane stay live across the third exponentiation).
+// With s = first chunk, A = s^-u, B = A^2, D = B^3, E = D^-u, G = (E^2)^-u and K = conj(G) E conj(D), the
+// reference computes   frob3(conj(s) K B) * frob2(K) * frob1(K B) * (s K E).   Frobenius is a ring homomorphism, so this
+// equals   [frob3(conj(s) B) * frob1(B) * s E] * K * frob1(K) * frob2(K) * frob3(K)   : the bracket (C below) and
+// E conj(D) are formed BEFORE the third exponentiation.  Gt elements are canonical, so the bytes are identical.
 template <class Ctx>
 BN_HD Fp2 hx_final_exp(const Ctx& c, const Fp2& f) {
     // first chunk
@@ -371,28 +392,26 @@ BN_HD Fp2 hx_final_exp(const Ctx& c, const Fp2& f) {
         s = hx_mul(c, d, cc);
     }
     // last chunk
+    c.park(HX_PARK_X, s);
     Fp2 a = hx_exp_by_neg_z(c, s);
     Fp2 b = hx_cyc_sqr(c, a);
-    Fp2 cq = hx_cyc_sqr(c, b);
-    Fp2 d = hx_mul(c, cq, b);
-    Fp2 e = hx_exp_by_neg_z(c, d);
-    Fp2 ff = hx_cyc_sqr(c, e);
-    Fp2 g = hx_exp_by_neg_z(c, ff);
-    Fp2 h = hx_conj(c, d);
-    Fp2 i = hx_conj(c, g);
-    Fp2 j = hx_mul(c, i, e);
-    Fp2 kk = hx_mul(c, j, h);
-    Fp2 l = hx_mul(c, kk, b);
-    Fp2 m = hx_mul(c, kk, e);
-    Fp2 n = hx_mul(c, s, m);
-    Fp2 o = hx_frob(c, l, 1);
-    Fp2 p = hx_mul(c, o, n);
-    Fp2 q = hx_frob(c, kk, 2);
-    Fp2 r = hx_mul(c, q, p);
-    Fp2 ss = hx_conj(c, s);
-    Fp2 t = hx_mul(c, ss, l);
-    Fp2 u = hx_frob(c, t, 3);
-    return hx_mul(c, u, r);
+    Fp2 d = hx_mul(c, hx_cyc_sqr(c, b), b);
+    c.park(HX_PARK_Y, b);
+    Fp2 e = hx_exp_by_neg_z(c, d);                                   // parked: s, b;  slot A holds d afterwards
+    Fp2 ed = hx_mul(c, e, hx_conj(c, c.unpark(HX_PARK_A)));           // E conj(D)
+    {
+        Fp2 sv = c.unpark(HX_PARK_X), bv = c.unpark(HX_PARK_Y);
+        Fp2 cst = hx_mul(c, hx_frob(c, hx_mul(c, hx_conj(c, sv), bv), 3), hx_frob(c, bv, 1));
+        cst = hx_mul(c, cst, hx_mul(c, sv, e));                       // C
+        c.park(HX_PARK_Y, cst);
+    }
+    c.park(HX_PARK_X, ed);
+    Fp2 g = hx_exp_by_neg_z(c, hx_cyc_sqr(c, e));                    // parked: E conj(D), C
+    Fp2 kk = hx_mul(c, hx_conj(c, g), c.unpark(HX_PARK_X));          // K
+    Fp2 r = hx_mul(c, c.unpark(HX_PARK_Y), kk);
+    r = hx_mul(c, r, hx_frob(c, kk, 1));
+    r = hx_mul(c, r, hx_frob(c, kk, 2));
+    return hx_mul(c, r, hx_frob(c, kk, 3));
 }
 
 // Gt::pow, reference src/fields/mod.rs:35-46 via src/lib.rs:171: 256 squarings, generic (non-cyclotomic).

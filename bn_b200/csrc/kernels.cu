@@ -145,7 +145,24 @@ struct DevCtx {
     uint32_t mine;     // shared address of this lane's exchange slots
     uint32_t hexbase;  // shared address of lane 0 of this hexad
     uint32_t kq;       // shared address of the k*q table
+    uint32_t parkbase; // shared address of this lane's parking area (0: kernel has none); layout [slot][16-byte piece][lane]
     __device__ __forceinline__ int k() const { return kk; }
+    __device__ __forceinline__ void park(int s, const Fp2& v) const {
+        const uint32_t a = parkbase + s * (4 * 32 * 16);
+        sts128(a, v.c0.v);
+        sts128(a + 512, v.c0.v + 4);
+        sts128(a + 1024, v.c1.v);
+        sts128(a + 1536, v.c1.v + 4);
+    }
+    __device__ __forceinline__ Fp2 unpark(int s) const {
+        const uint32_t a = parkbase + s * (4 * 32 * 16);
+        Fp2 r;
+        lds128(a, r.c0.v);
+        lds128(a + 512, r.c0.v + 4);
+        lds128(a + 1024, r.c1.v);
+        lds128(a + 1536, r.c1.v + 4);
+        return r;
+    }
     __device__ __forceinline__ Fp2 mul_xi(const Fp2& a) const { return fp2_mul_xi_r(a, KqRowLds{kq}); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ void put(int s, const Fp2& v) const { sts_fp2(mine + s * 64, v); }
@@ -163,12 +180,14 @@ struct DevCtx {
 struct DevLineSrc {
     const uint32_t* base;
     size_t n, pidx;
-    __device__ __forceinline__ void get(int t, int k, Fp2& l0, Fp2& l3k, Fp2& l4k) const {
-        const uint32_t* L = base + ((size_t)t * n + pidx) * BN_LINE_WORDS;
-        l0 = ld_fp2(L + BN_LINE_OFF_L0);
-        l3k = ld_fp2(L + (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3));
-        l4k = ld_fp2(L + (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4));
+    int k;
+    typedef const uint32_t* Handle;
+    __device__ __forceinline__ Handle acquire(int t) const { return base + ((size_t)t * n + pidx) * BN_LINE_WORDS; }
+    __device__ __forceinline__ Fp2 coef(Handle L, int i) const {
+        const int off = i == 0 ? BN_LINE_OFF_L0 : i == 1 ? (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3) : (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4);
+        return ld_fp2(L + off);
     }
+    __device__ __forceinline__ void release(int) const {}
 };
 #if BN_LINE_TMA
 // Line source fed by the TMA engine: one elected lane per warp issues a 1600-byte cp.async.bulk for Miller step t+2
@@ -179,6 +198,7 @@ struct DevLineSrcTma {
     size_t row_words;       // n * 80
     uint32_t ring;          // shared address of this warp's LineRing (buf[0], buf[1], bar[0], bar[1])
     uint32_t lane_off;      // byte offset of this lane's hexad inside a ring buffer
+    uint32_t coef_off;      // see coef()
     int lane;
     __device__ __forceinline__ uint32_t bar(int b) const { return ring + 2 * HEX_LINE_BYTES + 8 * b; }
     __device__ __forceinline__ uint32_t buf(int b) const { return ring + b * HEX_LINE_BYTES; }
@@ -202,7 +222,8 @@ struct DevLineSrcTma {
                          : "memory");
         }
     }
-    __device__ __forceinline__ void get(int t, int k, Fp2& l0, Fp2& l3k, Fp2& l4k) const {
+    typedef uint32_t Handle;  // shared address of this lane's line inside the ring buffer
+    __device__ __forceinline__ Handle acquire(int t) const {
         const uint32_t parity = (uint32_t)(t >> 1) & 1u;
         uint32_t ok = 0;
         for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
@@ -212,10 +233,11 @@ struct DevLineSrcTma {
                          : "memory");
         }
         if (!ok) __trap();
-        const uint32_t L = buf(t & 1) + lane_off;
-        l0 = lds_fp2(L + 4 * BN_LINE_OFF_L0);
-        l3k = lds_fp2(L + 4 * (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3));
-        l4k = lds_fp2(L + 4 * (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4));
+        return buf(t & 1) + lane_off;
+    }
+    // coef_off: byte offsets of l0 | l3k | l4k for this lane, packed 10 bits each
+    __device__ __forceinline__ Fp2 coef(Handle L, int i) const { return lds_fp2(L + ((coef_off >> (10 * i)) & 0x3ffu)); }
+    __device__ __forceinline__ void release(int t) const {
         __syncwarp();  // every lane has read buffer t&1 -> it can be refilled
         if (t + 2 < BN_NUM_LINES) issue(t + 2);
     }
@@ -465,8 +487,14 @@ __global__ void __launch_bounds__(DUO_BLOCK) k_pair_lines_duo(const uint32_t* __
 }
 
 #ifndef HEX_MIN_BLOCKS
-#define HEX_MIN_BLOCKS 1   // blocks/SM promised to ptxas for the hexad kernels (register cap = 65536 / (threads * blocks))
+#define HEX_MIN_BLOCKS 3   // blocks/SM promised to ptxas for k_miller_fexp (register cap = 65536 / (threads * blocks))
 #endif
+#ifndef HEX_MIN_BLOCKS_POW
+#define HEX_MIN_BLOCKS_POW 1   // the fused pairing.pow kernel keeps four more Gt values live
+#endif
+#define HEX_PARK_WARP_BYTES (HX_PARK_SLOTS * 4 * 32 * 16)
+#define HEX_DYN_SMEM_BYTES (sizeof(HexSmem) + HEX_WARPS_PER_BLOCK * HEX_PARK_WARP_BYTES)
+extern __shared__ __align__(128) unsigned char hex_dyn_smem[];
 
 struct HexIndex {
     DevCtx ctx;
@@ -487,47 +515,88 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     // the two spare lanes (30, 31) write their own slots but read hexad 4's, so every read stays inside the warp's area
     h.ctx.hexbase = smem_u32(sm->xch[warp] + (hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * 6 * HEX_LANE_STRIDE);
     h.ctx.kq = smem_u32(sm->kq);
+    h.ctx.parkbase = 0;
     size_t idx = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP + hex;
     h.active = (hex < HEX_PER_WARP) && (idx < n);
     h.pidx = h.active ? idx : (n - 1);
     return h;
 }
 
-// K4b: Miller loop + final exponentiation, one hexad per pairing.  POW: additionally raise the result to the
-// per-pairing scalar k (fused pairing(p, q).pow(k), row f-1).
-template <bool POW>
-__device__ __forceinline__ void miller_fexp_body(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags,
-                                                 const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
-    __shared__ HexSmem smem;
-    HexIndex h = hex_index(n, &smem);
+// K4b: Miller loop and final exponentiation, one hexad per pairing, as TWO kernels (k_miller writes the unreduced
+// Miller value into the output buffer, k_fexp finishes it in place): each kernel's hot code (about 30 KB) stays inside
+// the SM's instruction cache and all resident warps run the same phase -- with the fused form (BN_SPLIT_KERNELS=0,
+// k_miller_fexp) a third block per SM stalls on instruction fetch (profiles/README.md, runs 27-28).
+// POW: additionally raise the result to the per-pairing scalar k (fused pairing(p, q).pow(k), row f-1).
+#ifndef BN_SPLIT_KERNELS
+#define BN_SPLIT_KERNELS 1
+#endif
+#ifndef MILLER_MIN_BLOCKS
+#define MILLER_MIN_BLOCKS 3   // run 28: k_miller 2.31 ms at 3 blocks/SM vs 2.38 ms at 2
+#endif
+#ifndef FEXP_MIN_BLOCKS
+#define FEXP_MIN_BLOCKS 2   // run 28: k_fexp 4.11 ms at 2 blocks/SM (254 registers) vs 4.37 ms at 3 (168 registers, L0 instruction-cache misses)
+#endif
+__device__ __forceinline__ HexIndex hex_index_dyn(size_t n) {
+    // dynamic shared memory: HexSmem, then the parking area (HX_PARK_SLOTS x 64 B per lane, hexad.cuh)
+    HexSmem* smem = reinterpret_cast<HexSmem*>(hex_dyn_smem);
+    HexIndex h = hex_index(n, smem);
+    h.ctx.parkbase = smem_u32(hex_dyn_smem + sizeof(HexSmem)) + (threadIdx.x >> 5) * HEX_PARK_WARP_BYTES + (threadIdx.x & 31) * 16;
+    return h;
+}
+__device__ __forceinline__ Fp2 miller_part(const HexIndex& h, const uint32_t* __restrict__ lines, size_t n) {
 #if BN_LINE_TMA
+    HexSmem* smem = reinterpret_cast<HexSmem*>(hex_dyn_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     size_t p0 = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP;
     if (p0 >= n) p0 = n >= HEX_PER_WARP ? n - HEX_PER_WARP : 0;  // warp with no real pairing: any valid rows will do
     const int hex = lane / 6;
-    DevLineSrcTma src{lines + p0 * BN_LINE_WORDS, n * (size_t)BN_LINE_WORDS, smem_u32(&smem.ring[warp]),
-                      (uint32_t)((hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * BN_LINE_WORDS * 4), lane};
+    DevLineSrcTma src{lines + p0 * BN_LINE_WORDS, n * (size_t)BN_LINE_WORDS, smem_u32(&smem->ring[warp]),
+                      (uint32_t)((hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * BN_LINE_WORDS * 4),
+                      (uint32_t)(4 * BN_LINE_OFF_L0) | ((uint32_t)(4 * (h.ctx.kk < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3)) << 10) |
+                          ((uint32_t)(4 * (h.ctx.kk < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4)) << 20),
+                      lane};
     src.init();
 #else
-    DevLineSrc src{lines, n, h.pidx};
+    DevLineSrc src{lines, n, h.pidx, h.ctx.kk};
 #endif
-    Fp2 f = hx_miller_loop(h.ctx, src);
+    return hx_miller_loop(h.ctx, src);
+}
+template <bool POW>
+__device__ __forceinline__ Fp2 fexp_part(const HexIndex& h, Fp2 f, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k) {
     f = hx_final_exp(h.ctx, f);
     if (!flags[h.pidx]) f = hx_one(h.ctx);  // infinity => Gt::one(), reference src/groups/mod.rs:765-766
     if (POW) {
         Fp e = fp_from_mont<ModR>(ld_fp(k + h.pidx * 8));  // U256::from(Fr), reference src/fields/fp.rs:15-22
         f = hx_pow_cyc(h.ctx, f, e);
     }
+    return f;
+}
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, MILLER_MIN_BLOCKS)
+k_miller(const uint32_t* __restrict__ lines, uint32_t* __restrict__ out, size_t n) {
+    HexIndex h = hex_index_dyn(n);
+    Fp2 f = miller_part(h, lines, n);
     if (h.active) st_fp2(out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk), f);
 }
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, FEXP_MIN_BLOCKS)
+k_fexp(const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
+    HexIndex h = hex_index_dyn(n);
+    uint32_t* p = out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk);
+    Fp2 f = fexp_part<false>(h, ld_fp2(p), flags, nullptr);
+    if (h.active) st_fp2(p, f);
+}
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS_POW)
+k_fexp_pow(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
+    HexIndex h = hex_index_dyn(n);
+    uint32_t* p = out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk);
+    Fp2 f = fexp_part<true>(h, ld_fp2(p), flags, k);
+    if (h.active) st_fp2(p, f);
+}
+// fused single-kernel form (A/B: BN_SPLIT_KERNELS=0)
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
 k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
-    miller_fexp_body<false>(lines, flags, nullptr, out, n);
-}
-__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
-k_miller_fexp_pow(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k,
-                  uint32_t* __restrict__ out, size_t n) {
-    miller_fexp_body<true>(lines, flags, k, out, n);
+    HexIndex h = hex_index_dyn(n);
+    Fp2 f = fexp_part<false>(h, miller_part(h, lines, n), flags, nullptr);
+    if (h.active) st_fp2(out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk), f);
 }
 
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
@@ -580,7 +649,7 @@ struct State {
     size_t stage_cap[3] = {0, 0, 0};
     bool profiling = false;
     bool lines_duo = true;  // line kernel mapping: lane pair per pairing (default) or one thread per pairing
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before lines | before Miller | after the last kernel | before final exp
     bool ev_valid = false;
     cudaStream_t ev_stream = nullptr;
 };
@@ -641,12 +710,25 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_
     else
         k_pair_lines<<<blocks_for(n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
     if (g.profiling) CU(cudaEventRecord(g.ev[1], st));
+    const unsigned hb = blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), ht = 32 * HEX_WARPS_PER_BLOCK;
+#if BN_SPLIT_KERNELS
+    k_miller<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.lines, W(d_out), n);
+    if (g.profiling) CU(cudaEventRecord(g.ev[3], st));
     if (d_k)
-        k_miller_fexp_pow<<<blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), 32 * HEX_WARPS_PER_BLOCK, 0, st>>>(
-            g.lines, g.flags, W(d_k), W(d_out), n);
+        k_fexp_pow<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, W(d_k), W(d_out), n);
     else
-        k_miller_fexp<<<blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), 32 * HEX_WARPS_PER_BLOCK, 0, st>>>(
-            g.lines, g.flags, W(d_out), n);
+        k_fexp<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, W(d_out), n);
+    g_launches += 1;
+#else
+    if (g.profiling) CU(cudaEventRecord(g.ev[3], st));
+    if (d_k) {
+        k_miller<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.lines, W(d_out), n);
+        k_fexp_pow<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, W(d_k), W(d_out), n);
+        g_launches += 1;
+    } else {
+        k_miller_fexp<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.lines, g.flags, W(d_out), n);
+    }
+#endif
     if (g.profiling) {
         CU(cudaEventRecord(g.ev[2], st));
         g.ev_valid = true;
@@ -689,7 +771,14 @@ int bn_b200_init(int device) {
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(BN_B200_ENODEV, "device is not sm_100-class; kernels are built for sm_100a only");
     if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; i++)
+    CU(cudaFuncSetAttribute(k_miller_fexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_fexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_fexp_pow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_miller_fexp, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_miller, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_fexp, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    for (int i = 0; i < 4; i++)
         if (!g.ev[i]) CU(cudaEventCreate(&g.ev[i]));
     if (const char* e = getenv("BN_B200_LINES")) g.lines_duo = strcmp(e, "solo") != 0;  // A/B switch, both are bit-exact
     g.device = device;
@@ -704,10 +793,10 @@ int bn_b200_shutdown(void) {
     cudaStreamSynchronize(g.stream);
     if (g.lines) cudaFree(g.lines);
     if (g.flags) cudaFree(g.flags);
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 3; i++)
         if (g.stage[i]) cudaFree(g.stage[i]);
+    for (int i = 0; i < 4; i++)
         if (g.ev[i]) cudaEventDestroy(g.ev[i]);
-    }
     cudaStreamDestroy(g.stream);
     g = State();
     return 0;
@@ -733,6 +822,18 @@ int bn_b200_last_pairing_kernel_ms(float ms[2]) {
     CU(cudaEventSynchronize(g.ev[2]));
     CU(cudaEventElapsedTime(&ms[0], g.ev[0], g.ev[1]));
     CU(cudaEventElapsedTime(&ms[1], g.ev[1], g.ev[2]));
+    return 0;
+}
+int bn_b200_last_pairing_kernel_ms3(float ms[3]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!ms) return fail(BN_B200_EINVAL, "null output");
+    if (!g.ev_valid) return fail(BN_B200_EINVAL, "no profiled pairing call recorded (call bn_b200_set_profiling(1) first)");
+    CU(cudaEventSynchronize(g.ev[2]));
+    CU(cudaEventElapsedTime(&ms[0], g.ev[0], g.ev[1]));
+    CU(cudaEventElapsedTime(&ms[1], g.ev[1], g.ev[3]));
+    CU(cudaEventElapsedTime(&ms[2], g.ev[3], g.ev[2]));
     return 0;
 }
 

@@ -9,46 +9,44 @@
 
 namespace bn {
 
-// LineSrc::get(t, k, l0, l3k, l4k): fetch line t with the xi-variants lane k needs
-//   l3k = (k < 3 ? xi*l3 : l3),  l4k = (k < 4 ? xi*l4 : l4)
+// LineSrc:  Handle acquire(t)        wait until line t is readable
+//           Fp2 coef(h, i)            i = 0: l0, 1: l3k = (k < 3 ? xi*l3 : l3), 2: l4k = (k < 4 ? xi*l4 : l4) for this lane
+//           void release(t)           line t has been consumed (the device ring refills its buffer with line t + 2)
 template <class Ctx, class LineSrc>
 BN_HD Fp2 hx_miller_loop(const Ctx& c, const LineSrc& src) {
-    Fp2 l0, l3k, l4k;
     int t = 0;
     // first iteration: f = 1, so f^2 * line is the line itself: l0 + l3 w^3 + l4 w^4 (lanes 3 and 4 hold the
-    // plain l3 / l4 variants, see LineSrc::get)
-    src.get(t++, c.k(), l0, l3k, l4k);
-    Fp2 f = fp2_select(c.k() == 0, l0, fp2_select(c.k() == 3, l3k, fp2_select(c.k() == 4, l4k, fp2_zero())));
+    // plain l3 / l4 variants, see LineSrc::coef)
+    Fp2 f;
+    {
+        typename LineSrc::Handle h = src.acquire(t);
+        const int k = c.k();
+        f = src.coef(h, k == 3 ? 1 : (k == 4 ? 2 : 0));
+        f = fp2_select(k == 0 || k == 3 || k == 4, f, fp2_zero());
+        src.release(t++);
+    }
+    auto line_step = [&](Fp2 v) {
+        typename LineSrc::Handle h = src.acquire(t);
+        Fp2 r = hx_mul_line(c, v, src, h);
+        src.release(t++);
+        return r;
+    };
 #if BN_ATE_NAF
     // digit BN_ATE_NAF_DIGITS-1 (= 64) is zero: no addition after the first doubling
     for (int b = BN_ATE_NAF_DIGITS - 2; b >= 0; b--) {
         f = hx_sqr(c, f);
-        src.get(t++, c.k(), l0, l3k, l4k);
-        f = hx_mul_line(c, f, l0, l3k, l4k);
-        if ((BN_ATE_NAF_NZ >> b) & 1ULL) {
-            src.get(t++, c.k(), l0, l3k, l4k);
-            f = hx_mul_line(c, f, l0, l3k, l4k);
-        }
+        f = line_step(f);
+        if ((BN_ATE_NAF_NZ >> b) & 1ULL) f = line_step(f);
     }
 #else
-    if ((BN_ATE_BITS >> (BN_ATE_NBITS - 1)) & 1ULL) {
-        src.get(t++, c.k(), l0, l3k, l4k);
-        f = hx_mul_line(c, f, l0, l3k, l4k);
-    }
+    if ((BN_ATE_BITS >> (BN_ATE_NBITS - 1)) & 1ULL) f = line_step(f);
     for (int b = BN_ATE_NBITS - 2; b >= 0; b--) {
         f = hx_sqr(c, f);
-        src.get(t++, c.k(), l0, l3k, l4k);
-        f = hx_mul_line(c, f, l0, l3k, l4k);
-        if ((BN_ATE_BITS >> b) & 1ULL) {
-            src.get(t++, c.k(), l0, l3k, l4k);
-            f = hx_mul_line(c, f, l0, l3k, l4k);
-        }
+        f = line_step(f);
+        if ((BN_ATE_BITS >> b) & 1ULL) f = line_step(f);
     }
 #endif
-    for (int e = 0; e < 2; e++) {
-        src.get(t++, c.k(), l0, l3k, l4k);
-        f = hx_mul_line(c, f, l0, l3k, l4k);
-    }
+    for (int e = 0; e < 2; e++) f = line_step(f);
     return f;
 }
 

@@ -111,9 +111,11 @@ int bn_b200_imad_peak_dev(uint32_t* d_scratch, uint32_t blocks, uint32_t iters, 
 
 /* Per-kernel device timing of the most recent pairing_batch[_dev] call, measured with CUDA events on the
  * stream the kernels were launched on (enable first; reading synchronises that stream).
- * ms[0] = line-schedule kernel, ms[1] = Miller-loop + final-exponentiation kernel. */
+ * ms[0] = line-schedule kernel, ms[1] = Miller-loop + final-exponentiation kernels (two launches since run 28). */
 int bn_b200_set_profiling(int enable);
 int bn_b200_last_pairing_kernel_ms(float ms[2]);
+/* Same, three values: ms[0] = line schedule, ms[1] = Miller loop (k_miller), ms[2] = final exponentiation (k_fexp). */
+int bn_b200_last_pairing_kernel_ms3(float ms[3]);
 /* Number of kernels this library has launched since init (for the bench's gpu_launches claim). */
 unsigned long long bn_b200_launch_count(void);
 

@@ -34,6 +34,7 @@ struct Barrier {
 
 struct HostHexShared {
     Fp2 slot[6][3];
+    Fp2 parked[6][HX_PARK_SLOTS];
     Barrier bar{6};
 };
 
@@ -51,6 +52,8 @@ struct HostCtx {
     void put(int s, const Fp2& v) const { sh->slot[kk][s] = v; }
     Fp2 get(int src, int s) const { return sh->slot[src][s]; }
     void sync() const { sh->bar.wait(); }
+    void park(int s, const Fp2& v) const { sh->parked[kk][s] = v; }
+    Fp2 unpark(int s) const { return sh->parked[kk][s]; }
 };
 
 struct HostDuoShared {
@@ -98,12 +101,15 @@ void run_hexad(Fn fn) {
 
 struct HostLineSrc {
     const uint64_t* lines;  // [BN_NUM_LINES][40] u64
-    void get(int t, int k, Fp2& l0, Fp2& l3k, Fp2& l4k) const {
-        const uint64_t* L = lines + (size_t)t * 40;
-        l0 = load_fp2(L + BN_LINE_OFF_L0 / 2);
-        l3k = load_fp2(L + (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3) / 2);
-        l4k = load_fp2(L + (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4) / 2);
+    int k;
+    typedef const uint64_t* Handle;
+    Handle acquire(int t) const { return lines + (size_t)t * 40; }
+    Fp2 coef(Handle L, int i) const {
+        if (i == 0) return load_fp2(L + BN_LINE_OFF_L0 / 2);
+        if (i == 1) return load_fp2(L + (k < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3) / 2);
+        return load_fp2(L + (k < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4) / 2);
     }
+    void release(int) const {}
 };
 
 struct HostLineSink {
@@ -235,7 +241,7 @@ void emu_gt_op(int op, const uint64_t* a, const uint64_t* b, int arg, uint64_t* 
 // Miller loop only (unreduced), from stored lines
 void emu_miller(const uint64_t* lines, uint64_t* out) {
     run_hexad([&](HostCtx& c) {
-        HostLineSrc src{lines};
+        HostLineSrc src{lines, c.k()};
         Fp2 f = hx_miller_loop(c, src);
         store_fp2(out + 8 * gt_slot(c.k()), f);
     });
@@ -245,7 +251,7 @@ void emu_pairing(const uint64_t* g1, const uint64_t* g2, uint64_t* out) {
     std::vector<uint64_t> lines(BN_NUM_LINES * 40);
     int finite = emu_lines(g1, g2, lines.data(), nullptr, nullptr);
     run_hexad([&](HostCtx& c) {
-        HostLineSrc src{lines.data()};
+        HostLineSrc src{lines.data(), c.k()};
         Fp2 f = hx_miller_loop(c, src);
         f = hx_final_exp(c, f);
         if (!finite) f = hx_one(c);
