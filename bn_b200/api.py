@@ -132,6 +132,51 @@ def g2_check_batch(g2, device: int = 0) -> np.ndarray:
     return ok.astype(bool)
 
 
+WIRE_BYTES = {"g1": 65, "g2": 129, "fr": 32}
+_WIRE_WORDS = {"g1": G1_WORDS, "g2": G2_WORDS, "fr": FR_WORDS}
+WIRE_ERRORS = {1: "invalid leading byte for uncompressed group element", 2: "integer is not less than modulus",
+               3: "point is not on the curve", 4: "point is not in the subgroup"}
+
+
+def encode_batch(kind: str, img, device: int = 0) -> np.ndarray:
+    """Wire records [n, 65 | 129 | 32] uint8 of G1 / G2 / Fr images (reference RustcEncodable impls:
+    src/groups/mod.rs:143-163, src/fields/fq2.rs:31-40, src/fields/fp.rs:24-29).  Infinity = 0x00 + zero padding."""
+    lib = _lib.init(device)
+    img = _arr(img, _WIRE_WORDS[kind])
+    out = np.zeros((len(img), WIRE_BYTES[kind]), dtype=np.uint8)
+    _lib.check(getattr(lib, "bn_b200_%s_encode_batch" % kind)(_p(img), _p(out), ctypes.c_size_t(len(img))))
+    return out
+
+
+def decode_batch(kind: str, records, device: int = 0):
+    """Wire records -> (images, status[n]); status 0 = ok, else a key of WIRE_ERRORS (reference RustcDecodable impls:
+    src/groups/mod.rs:178-205, src/fields/fq2.rs:42-53, src/fields/fp.rs:31-36)."""
+    lib = _lib.init(device)
+    rec = np.ascontiguousarray(records, dtype=np.uint8)
+    if rec.ndim != 2 or rec.shape[1] != WIRE_BYTES[kind]:
+        raise ValueError("expected [n,%d] uint8 records, got %s" % (WIRE_BYTES[kind], rec.shape))
+    out = np.empty((len(rec), _WIRE_WORDS[kind]), dtype=np.uint64)
+    status = np.zeros(len(rec), dtype=np.uint8)
+    _lib.check(getattr(lib, "bn_b200_%s_decode_batch" % kind)(_p(rec), _p(out), _p(status), ctypes.c_size_t(len(rec))))
+    return out, status
+
+
+def to_wire(kind: str, record: np.ndarray) -> bytes:
+    """The exact reference byte string of one record (infinity is the single byte 0x00)."""
+    b = bytes(record)
+    return b[:1] if kind != "fr" and b[0] == 0 else b
+
+
+def from_wire(kind: str, data: bytes) -> np.ndarray:
+    """One reference byte string -> fixed-stride record (zero padded)."""
+    r = np.zeros(WIRE_BYTES[kind], dtype=np.uint8)
+    d = np.frombuffer(data, dtype=np.uint8)
+    if len(d) > len(r):
+        raise ValueError("record too long")
+    r[:len(d)] = d
+    return r
+
+
 def fq_mul_chain(a, b, iters: int, device: int = 0) -> np.ndarray:
     """x <- x*b (Montgomery mod q) `iters` times per element (BASELINE config 2)."""
     lib = _lib.init(device)

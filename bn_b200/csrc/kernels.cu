@@ -23,6 +23,7 @@
 
 #include "../../include/bn_b200.h"
 #include "pairing.cuh"
+#include "wire.cuh"
 
 using namespace bn;
 
@@ -402,6 +403,65 @@ __global__ void __launch_bounds__(128) k_g2_check(const uint32_t* __restrict__ p
         good = fp2_is_zero(r.z);
     }
     ok[i] = (fp2_is_zero(P.z) || good) ? 1 : 0;
+}
+
+// ---- row f-3: wire format (wire.cuh), one thread per element ------------------------------------------------------
+// encode = Group::normalize + from-Montgomery + big-endian bytes (reference src/groups/mod.rs:143-163);
+// decode = bytes -> Montgomery + the reference's validity checks, status per element (src/groups/mod.rs:178-205).
+__global__ void __launch_bounds__(128) k_g1_encode(const uint32_t* __restrict__ p, uint8_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x = ld_fp(p + i * 24), y = ld_fp(p + i * 24 + 8), z = ld_fp(p + i * 24 + 16);
+    const bool inf = fp_is_zero(z);
+    if (!inf && !fp_eq(z, fq_one())) {
+        Fp zi = fp_inv<MQ>(z), zi2 = fp_mul<MQ>(zi, zi);
+        x = fp_mul<MQ>(x, zi2);
+        y = fp_mul<MQ>(y, fp_mul<MQ>(zi2, zi));
+    }
+    g1_encode_affine(x, y, inf, out + i * 65);
+}
+__global__ void __launch_bounds__(128) k_g2_encode(const uint32_t* __restrict__ p, uint8_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp2 x = ld_fp2(p + i * 48), y = ld_fp2(p + i * 48 + 16), z = ld_fp2(p + i * 48 + 32);
+    const bool inf = fp2_is_zero(z);
+    if (!inf && !fp2_eq(z, fp2_one())) {
+        Fp2 zi = fp2_inv(z), zi2 = fp2_sqr(zi);
+        x = fp2_mul(x, zi2);
+        y = fp2_mul(y, fp2_mul(zi2, zi));
+    }
+    g2_encode_affine(x, y, inf, out + i * 129);
+}
+__global__ void __launch_bounds__(128) k_g1_decode(const uint8_t* __restrict__ in, uint32_t* __restrict__ out, uint8_t* __restrict__ status, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Jac<FqOps> P;
+    status[i] = g1_decode(in + i * 65, P);
+    st_fp(out + i * 24, P.x);
+    st_fp(out + i * 24 + 8, P.y);
+    st_fp(out + i * 24 + 16, P.z);
+}
+__global__ void __launch_bounds__(128) k_g2_decode(const uint8_t* __restrict__ in, uint32_t* __restrict__ out, uint8_t* __restrict__ status, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Jac<Fq2Ops> P;
+    status[i] = g2_decode(in + i * 129, P);
+    st_fp2(out + i * 48, P.x);
+    st_fp2(out + i * 48 + 16, P.y);
+    st_fp2(out + i * 48 + 32, P.z);
+}
+__global__ void __launch_bounds__(128) k_fr_encode(const uint32_t* __restrict__ a, uint8_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_encode<ModR>(ld_fp(a + i * 8), out + i * 32);
+}
+__global__ void __launch_bounds__(128) k_fr_decode(const uint8_t* __restrict__ in, uint32_t* __restrict__ out, uint8_t* __restrict__ status, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x;
+    const bool ok = fp_decode<ModR>(in + i * 32, x);
+    status[i] = ok ? WIRE_OK : WIRE_NOT_REDUCED;
+    st_fp(out + i * 8, ok ? x : fp_zero());
 }
 
 // K4a: one thread per pairing.  flags[p] = 1 when the pair is finite, 0 when either point is infinity.
@@ -1036,5 +1096,72 @@ DEFINE_CHECK(g1, k_g1_check, bn_g1)
 DEFINE_CHECK(g2, k_g2_check, bn_g2)
 DEFINE_NORMALIZE(g1, k_g1_normalize, bn_g1)
 DEFINE_NORMALIZE(g2, k_g2_normalize, bn_g2)
+
+
+// ---- wire format entry points (row f-3) ---------------------------------------------------------------------------
+#define DEFINE_ENCODE(NAME, KERNEL, T, REC)                                                                         \
+    int bn_b200_##NAME##_encode_batch_dev(const T* d_p, uint8_t* d_out, size_t n, void* stream) {                     \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
+        int rc = ensure_ready();                                                                                    \
+        if (rc) return rc;                                                                                          \
+        if (n && (!d_p || !d_out)) return fail(BN_B200_EINVAL, "null pointer");                                     \
+        if (n == 0) return 0;                                                                                       \
+        KERNEL<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(W(d_p), d_out, n);         \
+        g_launches += 1;                                                                                            \
+        CU(cudaGetLastError());                                                                                     \
+        return 0;                                                                                                   \
+    }                                                                                                               \
+    int bn_b200_##NAME##_encode_batch(const T* p, uint8_t* out, size_t n) {                                          \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
+        int rc = ensure_ready();                                                                                    \
+        if (rc) return rc;                                                                                          \
+        if (n == 0) return 0;                                                                                       \
+        if (!p || !out) return fail(BN_B200_EINVAL, "null pointer");                                                \
+        return host_call(p, n * sizeof(T), p, sizeof(T), out, n * (size_t)(REC),                                    \
+                         [&](void* x, void*, void* o, cudaStream_t st) {                                            \
+                             KERNEL<<<blocks_for(n, 128), 128, 0, st>>>(W(x), (uint8_t*)o, n);                      \
+                             g_launches += 1;                                                                       \
+                             CU(cudaGetLastError());                                                                \
+                             return 0;                                                                              \
+                         });                                                                                        \
+    }
+#define DEFINE_DECODE(NAME, KERNEL, T, REC)                                                                         \
+    int bn_b200_##NAME##_decode_batch_dev(const uint8_t* d_in, T* d_out, uint8_t* d_status, size_t n, void* stream) { \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
+        int rc = ensure_ready();                                                                                    \
+        if (rc) return rc;                                                                                          \
+        if (n && (!d_in || !d_out || !d_status)) return fail(BN_B200_EINVAL, "null pointer");                       \
+        if (n == 0) return 0;                                                                                       \
+        KERNEL<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(d_in, W(d_out), d_status, n); \
+        g_launches += 1;                                                                                            \
+        CU(cudaGetLastError());                                                                                     \
+        return 0;                                                                                                   \
+    }                                                                                                               \
+    int bn_b200_##NAME##_decode_batch(const uint8_t* in, T* out, uint8_t* status, size_t n) {                        \
+        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
+        int rc = ensure_ready();                                                                                    \
+        if (rc) return rc;                                                                                          \
+        if (n == 0) return 0;                                                                                       \
+        if (!in || !out || !status) return fail(BN_B200_EINVAL, "null pointer");                                    \
+        /* staging: records | points followed by the status bytes */                                               \
+        const size_t pts = n * sizeof(T);                                                                           \
+        if ((rc = ensure_buf(&g.stage[0], &g.stage_cap[0], n * (size_t)(REC)))) return rc;                          \
+        if ((rc = ensure_buf(&g.stage[2], &g.stage_cap[2], pts + n))) return rc;                                    \
+        CU(cudaMemcpyAsync(g.stage[0], in, n * (size_t)(REC), cudaMemcpyHostToDevice, g.stream));                   \
+        uint8_t* d_status = (uint8_t*)g.stage[2] + pts;                                                             \
+        KERNEL<<<blocks_for(n, 128), 128, 0, g.stream>>>((const uint8_t*)g.stage[0], W(g.stage[2]), d_status, n);   \
+        g_launches += 1;                                                                                            \
+        CU(cudaGetLastError());                                                                                     \
+        CU(cudaMemcpyAsync(out, g.stage[2], pts, cudaMemcpyDeviceToHost, g.stream));                                \
+        CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, g.stream));                                 \
+        CU(cudaStreamSynchronize(g.stream));                                                                        \
+        return 0;                                                                                                   \
+    }
+DEFINE_ENCODE(g1, k_g1_encode, bn_g1, 65)
+DEFINE_ENCODE(g2, k_g2_encode, bn_g2, 129)
+DEFINE_ENCODE(fr, k_fr_encode, bn_fr, 32)
+DEFINE_DECODE(g1, k_g1_decode, bn_g1, 65)
+DEFINE_DECODE(g2, k_g2_decode, bn_g2, 129)
+DEFINE_DECODE(fr, k_fr_decode, bn_fr, 32)
 
 }  // extern "C"

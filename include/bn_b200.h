@@ -100,6 +100,33 @@ int bn_b200_g1_check_batch_dev(const bn_g1* d_p, uint8_t* d_ok, size_t n, void* 
 int bn_b200_g2_check_batch(const bn_g2* p, uint8_t* ok, size_t n);
 int bn_b200_g2_check_batch_dev(const bn_g2* d_p, uint8_t* d_ok, size_t n, void* stream);
 
+/* Wire format (row f-3), fixed-stride records.  replaces the RustcEncodable / RustcDecodable impls of Fr, G1, G2
+ * (src/lib.rs:15, 79, 122 -> src/fields/fp.rs:24-36, src/fields/fq2.rs:31-53, src/groups/mod.rs:143-205; bincode adds no framing).
+ *   Fr : 32 bytes, big-endian canonical integer.
+ *   G1 : BN_B200_G1_WIRE_BYTES = 65 per record: 0x04 | x (32, BE) | y (32, BE).
+ *   G2 : BN_B200_G2_WIRE_BYTES = 129 per record: 0x04 | x (64, BE integer c1*q + c0) | y (64).
+ * The point at infinity is the single byte 0x00 on the wire; inside a fixed-stride record it is 0x00 followed by zero
+ * padding (encode) and only byte 0 is read (decode) -- a caller producing the exact reference stream emits record[0..1].
+ * encode normalises (to_affine) first.  decode writes (x, y, one) in Montgomery form, or zero() = (0, 1, 0) when the
+ * record is infinity or invalid, and a status per element:
+ *   0 ok | 1 invalid leading byte | 2 integer is not less than modulus | 3 not on the curve | 4 not in the subgroup (G2)
+ * -- the reference's Err cases, checked in the reference's order (src/groups/mod.rs:178-205). */
+#define BN_B200_G1_WIRE_BYTES 65
+#define BN_B200_G2_WIRE_BYTES 129
+#define BN_B200_FR_WIRE_BYTES 32
+int bn_b200_g1_encode_batch(const bn_g1* p, uint8_t* out, size_t n);
+int bn_b200_g1_encode_batch_dev(const bn_g1* d_p, uint8_t* d_out, size_t n, void* stream);
+int bn_b200_g2_encode_batch(const bn_g2* p, uint8_t* out, size_t n);
+int bn_b200_g2_encode_batch_dev(const bn_g2* d_p, uint8_t* d_out, size_t n, void* stream);
+int bn_b200_fr_encode_batch(const bn_fr* a, uint8_t* out, size_t n);
+int bn_b200_fr_encode_batch_dev(const bn_fr* d_a, uint8_t* d_out, size_t n, void* stream);
+int bn_b200_g1_decode_batch(const uint8_t* in, bn_g1* out, uint8_t* status, size_t n);
+int bn_b200_g1_decode_batch_dev(const uint8_t* d_in, bn_g1* d_out, uint8_t* d_status, size_t n, void* stream);
+int bn_b200_g2_decode_batch(const uint8_t* in, bn_g2* out, uint8_t* status, size_t n);
+int bn_b200_g2_decode_batch_dev(const uint8_t* d_in, bn_g2* d_out, uint8_t* d_status, size_t n, void* stream);
+int bn_b200_fr_decode_batch(const uint8_t* in, bn_fr* out, uint8_t* status, size_t n);
+int bn_b200_fr_decode_batch_dev(const uint8_t* d_in, bn_fr* d_out, uint8_t* d_status, size_t n, void* stream);
+
 /* x <- x * b (Montgomery, mod q) repeated `iters` times per element: the BASELINE config-2 microbenchmark of
  * the innermost operation (Fq Mul, src/fields/fp.rs:137-146 -> U256::mul src/arith.rs:257-263). a, b, out: n x 4 u64. */
 int bn_b200_fq_mul_chain(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, uint32_t iters);

@@ -99,3 +99,23 @@ def pairing(g1, g2, variant="product"):
     out = np.zeros(48, dtype=np.uint64)
     lib(variant).emu_pairing(_p(g1), _p(g2), _p(out))
     return out
+
+
+_WIRE = {"fr": (0, 4, 32), "g1": (1, 12, 65), "g2": (2, 24, 129)}
+
+
+def wire_encode(kind, img):
+    code, words, nbytes = _WIRE[kind]
+    img = _c(img)
+    rec = np.zeros(nbytes, dtype=np.uint8)
+    lib().emu_wire_encode(code, _p(img), rec.ctypes.data_as(ctypes.c_void_p))
+    return rec
+
+
+def wire_decode(kind, rec):
+    code, words, nbytes = _WIRE[kind]
+    rec = np.ascontiguousarray(rec, dtype=np.uint8)
+    assert rec.shape == (nbytes,)
+    img = np.zeros(words, dtype=np.uint64)
+    st = lib().emu_wire_decode(code, rec.ctypes.data_as(ctypes.c_void_p), _p(img))
+    return img, st

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../bn_b200/csrc/pairing.cuh"  // pulls in fp.cuh, fp2.cuh, duo.cuh, curve.cuh, hexad.cuh
+#include "../../bn_b200/csrc/wire.cuh"
 
 using namespace bn;
 
@@ -257,5 +258,49 @@ void emu_pairing(const uint64_t* g1, const uint64_t* g2, uint64_t* out) {
         if (!finite) f = hx_one(c);
         store_fp2(out + 8 * gt_slot(c.k()), f);
     });
+}
+// wire format (wire.cuh).  kind: 0 Fr, 1 G1, 2 G2.  encode: image (u64 LE words) -> record; decode: record -> image,
+// returns the status byte.
+void emu_wire_encode(int kind, const uint64_t* img, uint8_t* rec) {
+    if (kind == 0) {
+        fp_encode<ModR>(load_fp(img), rec);
+    } else if (kind == 1) {
+        Jac<FqOps> p = load_g1(img);
+        const bool inf = fp_is_zero(p.z);
+        Fp x = p.x, y = p.y;
+        if (!inf && !fp_eq(p.z, fq_one())) {
+            Fp zi = fp_inv<MQ>(p.z), zi2 = fp_mul<MQ>(zi, zi);
+            x = fp_mul<MQ>(x, zi2);
+            y = fp_mul<MQ>(y, fp_mul<MQ>(zi2, zi));
+        }
+        g1_encode_affine(x, y, inf, rec);
+    } else {
+        Jac<Fq2Ops> p = load_g2(img);
+        const bool inf = fp2_is_zero(p.z);
+        Fp2 x = p.x, y = p.y;
+        if (!inf && !fp2_eq(p.z, fp2_one())) {
+            Fp2 zi = fp2_inv(p.z), zi2 = fp2_sqr(zi);
+            x = fp2_mul(x, zi2);
+            y = fp2_mul(y, fp2_mul(zi2, zi));
+        }
+        g2_encode_affine(x, y, inf, rec);
+    }
+}
+int emu_wire_decode(int kind, const uint8_t* rec, uint64_t* img) {
+    if (kind == 0) {
+        Fp x;
+        const bool ok = fp_decode<ModR>(rec, x);
+        store_fp(img, ok ? x : fp_zero());
+        return ok ? WIRE_OK : WIRE_NOT_REDUCED;
+    } else if (kind == 1) {
+        Jac<FqOps> p;
+        int st = g1_decode(rec, p);
+        store_fp(img, p.x); store_fp(img + 4, p.y); store_fp(img + 8, p.z);
+        return st;
+    }
+    Jac<Fq2Ops> p;
+    int st = g2_decode(rec, p);
+    store_fp2(img, p.x); store_fp2(img + 8, p.y); store_fp2(img + 16, p.z);
+    return st;
 }
 }

@@ -53,7 +53,7 @@ template <int NM, int NA>
 __device__ __forceinline__ void unit(Regs& r) {
 #pragma unroll
     for (int i = 0; i < (NM > NA ? NM : NA); i++) {
-        if (i < NM) MADROW(r.m[i & 3], r.x[0], r.x[1], r.x[2], r.x[3], r.y);
+        if (i < NM) MADROW(r.m[i & 3], r.x[0], r.x[1], r.x[2], r.x[3], r.y + (i & 3));
         if (i < NA) ADD8(r.s[i & 3], r.s[(i + 1) & 3]);
     }
 }
