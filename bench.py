@@ -3,13 +3,13 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path (line schedule kernel + Miller/final-exponentiation kernel) over one batch
+One "step" = one pass of the hot path (line schedule, Miller loop and final-exponentiation kernels) over one batch
 of 2^14 synthetic (G1, G2) pairs per GPU (BASELINE config 4; N GPUs => N * 2^14 pairs, config 5's 2^17 at N = 8,
 weak scaling, plus an NCCL all-gather of the 384-byte Gt results).  Prints ONE JSON line on rank 0.
 
   value     whole-job pairings/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
   e2e       same metric through the host-buffer C ABI call (pinned host inputs, H2D + kernels + D2H each step)
-  roofline  dominant kernel (k_miller_fexp) against the integer-multiply (IMAD.WIDE.U32) issue peak measured
+  roofline  dominant kernel (k_fexp) against the integer-multiply (IMAD.WIDE.U32) issue peak measured
             live by the calibration kernel; HBM GB/s reported beside it (the path is not HBM-bound)
   cpu_baseline  the C restatement of the reference algorithm (oracle/bn_ref.c, "port") on this box's host cores
 
@@ -35,7 +35,9 @@ METRIC = "pairings/sec (batched optimal-ate)"
 # algorithmic work (SURVEY.md section 8d / BASELINE.md section 2): 136 IMAD per Fq multiplication
 IMAD_PER_M = 136
 M_PAIRING = 18995                 # real Fq mults per pairing
-M_MILLER_FEXP = 6690 + 227 + 8541  # miller_loop + final exponentiation (the k_miller_fexp kernel)
+M_MILLER = 6690                   # miller_loop (k_miller)
+M_FEXP = 227 + 8541               # final exponentiation (k_fexp)
+M_MILLER_FEXP = M_MILLER + M_FEXP
 M_LINES = 21 + 3516               # to_affine + line precomputation (the k_pair_lines kernel)
 BYTES_IN, BYTES_OUT = 288, 384    # per pairing
 
@@ -356,7 +358,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = 128 * cores
+        rate0, _ = cpu_reference_rate(64 * cores, cores)          # calibration
+        sample = max(64 * cores, int(rate0 * 12.0) // cores * cores)  # about 12 s of work on all host threads
         rate, dt = cpu_reference_rate(sample, cores)
         rate1, dt1 = cpu_reference_rate(128, 1)
         cpu = {"value": rate, "unit": "pairings/s", "cores": cores, "kind": "port",
@@ -365,7 +368,10 @@ def main():
                "single_thread_value": rate1}
 
     if rank == 0:
-        achieved = n / (ms_miller * 1e-3) * M_MILLER_FEXP * IMAD_PER_M  # algorithmic IMAD/s of the dominant kernel
+        # algorithmic IMAD/s per kernel (Fq mults of the reference algorithm x 136)
+        kern = {"k_pair_lines_duo": (ms_lines, M_LINES), "k_miller": (ms_mil, M_MILLER), "k_fexp": (ms_fexp, M_FEXP)}
+        dominant = max(kern, key=lambda k: kern[k][0])
+        achieved = n / (kern[dominant][0] * 1e-3) * kern[dominant][1] * IMAD_PER_M
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -373,14 +379,25 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None  # dram bytes read+written per launch of the dominant kernel, from the committed ncu capture
+        # committed ncu capture of this build (profiles/ncu_kernels.json): DRAM traffic and executed-instruction mix per launch
+        ncu = {}
         try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                tj = json.load(f)
-            traffic = {"bytes_per_launch": tj["k_miller_fexp"]["dram_read_bytes"] + tj["k_miller_fexp"]["dram_write_bytes"],
-                       "algorithmic_bytes_per_launch": n * (lib.bn_b200_num_lines() * 320 + BYTES_OUT), "source": tj["source"]}
+            with open(os.path.join(ROOT, "profiles", "ncu_kernels.json")) as f:
+                ncu = json.load(f)
         except Exception:
             pass
+        traffic = None
+        if dominant in ncu.get("kernels", {}):
+            traffic = ncu["kernels"][dominant]["dram_read_bytes"] + ncu["kernels"][dominant]["dram_write_bytes"]
+        # Issue-slot model (profiles/r01_run25_ubench_pipes.txt): on B200 the integer ALU and the
+        # fma-heavy pipe do not overlap for this instruction mix; a warp instruction costs ~4 issue cycles (IMAD.WIDE)
+        # or ~1.77 (everything else) per scheduler.  bound_ms = that sum over the executed instructions of the launch.
+        slot = {}
+        for k, v in ncu.get("kernels", {}).items():
+            if k in kern and "inst_imad_wide" in v:
+                cyc = (4.0 * v["inst_imad_wide"] + 1.77 * (v["inst_total"] - v["inst_imad_wide"])) / (lib.bn_b200_sm_count() * 4)
+                bound_ms = cyc / (clocks.get("sm_mhz", 1965) * 1e3) * (n / v.get("pairs", n))
+                slot[k] = {"bound_ms": bound_ms, "measured_ms": kern[k][0], "frac": bound_ms / kern[k][0]}
         line_bytes = lib.bn_b200_num_lines() * 320
         line = {
             "metric": METRIC, "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
@@ -394,20 +411,28 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": n * BYTES_IN,
                     "d2h_bytes_per_step": n * BYTES_OUT,
-                    "path": "bn_b200_pairing_batch (host pointers, pinned): H2D + 2 kernels + D2H per step"},
+                    "path": "bn_b200_pairing_batch (host pointers, pinned): H2D + 3 kernels + D2H per step"},
             "gpu_launches": int(launches),
             "roofline": {
-                "bound": "int-imad", "kernel": "k_miller_fexp",
+                "bound": "int-imad", "kernel": dominant,
                 "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s (IMAD.WIDE.U32 32x32+64)",
                 "frac": achieved / imad_peak,
-                "peak_source": "measured live, this run: k_imad_peak (pure IMAD.WIDE.U32.X carry chains), %d blocks x 256 thr. "
-                               "IMAD.WIDE issues at 8 lanes/clk/SMSP on B200 (148*4*8*1.965e9 = 9.31e12), half of SURVEY.md's "
-                               "nominal 18.6e12 assumption" % blocks,
-                "frac_of_survey_nominal_18.6T": achieved / 18.6e12,
-                "algorithmic": "%d Fq mults/pairing x 136 IMAD in this kernel (whole pairing: %d)" % (M_MILLER_FEXP, M_PAIRING),
                 "traffic": traffic,
+                "bound_note": "integer modular arithmetic: neither HBM- nor tensor-bound (SURVEY.md section 8d); the denominator is the "
+                              "IMAD.WIDE issue rate measured live by k_imad_peak (%d blocks x 256 threads): 8 lanes/clk/SMSP = "
+                              "148*4*8*1.965e9 = 9.31e12/s, half of SURVEY.md's nominal 18.6e12 assumption" % blocks,
+                "frac_of_survey_nominal_18.6T": achieved / 18.6e12,
+                "algorithmic": "Fq mults of the reference algorithm x 136 IMAD: lines %d, Miller loop %d, final exponentiation %d (pairing: %d)"
+                               % (M_LINES, M_MILLER, M_FEXP, M_PAIRING),
+                "kernels": {k: {"ms": v[0], "achieved_timad": n / (v[0] * 1e-3) * v[1] * IMAD_PER_M / 1e12,
+                                "frac": n / (v[0] * 1e-3) * v[1] * IMAD_PER_M / imad_peak} for k, v in kern.items()},
                 "kernel_ms": {"k_pair_lines": ms_lines, "k_miller_fexp": ms_miller, "k_miller": ms_mil, "k_fexp": ms_fexp},
                 "whole_path_frac": (n / ((ms_lines + ms_miller) * 1e-3)) * M_PAIRING * IMAD_PER_M / imad_peak,
+                "issue_slot_model": slot or None,
+                "traffic_detail": {"algorithmic_bytes_per_launch": {"k_pair_lines_duo": n * (BYTES_IN + line_bytes),
+                                                                    "k_miller": n * (line_bytes + BYTES_OUT), "k_fexp": n * 2 * BYTES_OUT},
+                                   "ncu": {k: {"dram_read_bytes": v.get("dram_read_bytes"), "dram_write_bytes": v.get("dram_write_bytes")}
+                                           for k, v in ncu.get("kernels", {}).items()}, "source": ncu.get("source")},
                 "hbm": {"achieved_gbs": n * (BYTES_IN + BYTES_OUT) / (ms_step * 1e-3) / 1e9,
                         "with_line_buffer_gbs": n * (BYTES_IN + BYTES_OUT + 2 * line_bytes) / (ms_step * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "of": "measured" if peaks else "fallback"},

@@ -113,4 +113,56 @@ inline std::vector<Gt> pow_batch(const std::vector<Gt>& a, const std::vector<Fr>
     return out;
 }
 
+// ---- wire format (RustcEncodable / RustcDecodable of G1, G2: src/groups/mod.rs:143-205) ----
+// encode: one byte string per point, exactly the reference's (0x00 for infinity, else 0x04 | x | y).
+// decode: throws bn::DecodeError with the reference's message for the first invalid element.
+struct DecodeError : std::runtime_error {
+    size_t index;
+    int status;
+    DecodeError(size_t i, int st)
+        : std::runtime_error(st == 1   ? "invalid leading byte for uncompressed group element"
+                             : st == 2 ? "integer is not less than modulus"
+                             : st == 3 ? "point is not on the curve"
+                                       : "point is not in the subgroup"),
+          index(i), status(st) {}
+};
+namespace detail {
+template <class P, class Raw, int REC>
+std::vector<std::string> encode(const std::vector<P>& p, int (*fn)(const Raw*, uint8_t*, size_t)) {
+    std::vector<uint8_t> rec(p.size() * REC);
+    check(fn(&p.data()->v, rec.data(), p.size()));
+    std::vector<std::string> out(p.size());
+    for (size_t i = 0; i < p.size(); i++) {
+        const char* r = reinterpret_cast<const char*>(rec.data() + i * REC);
+        out[i].assign(r, r[0] == 0 ? 1 : REC);
+    }
+    return out;
+}
+template <class P, class Raw, int REC>
+std::vector<P> decode(const std::vector<std::string>& w, int (*fn)(const uint8_t*, Raw*, uint8_t*, size_t)) {
+    std::vector<uint8_t> rec(w.size() * REC, 0), st(w.size());
+    for (size_t i = 0; i < w.size(); i++) {
+        if (w[i].empty() || w[i].size() > (size_t)REC || (w[i][0] != 0 && w[i].size() != (size_t)REC)) throw DecodeError(i, 1);
+        std::memcpy(rec.data() + i * REC, w[i].data(), w[i].size());
+    }
+    std::vector<P> out(w.size());
+    check(fn(rec.data(), &out.data()->v, st.data(), w.size()));
+    for (size_t i = 0; i < w.size(); i++)
+        if (st[i]) throw DecodeError(i, st[i]);
+    return out;
+}
+}  // namespace detail
+inline std::vector<std::string> encode_batch(const std::vector<G1>& p) {
+    return detail::encode<G1, bn_g1, BN_B200_G1_WIRE_BYTES>(p, bn_b200_g1_encode_batch);
+}
+inline std::vector<std::string> encode_batch(const std::vector<G2>& p) {
+    return detail::encode<G2, bn_g2, BN_B200_G2_WIRE_BYTES>(p, bn_b200_g2_encode_batch);
+}
+inline std::vector<G1> decode_g1_batch(const std::vector<std::string>& w) {
+    return detail::decode<G1, bn_g1, BN_B200_G1_WIRE_BYTES>(w, bn_b200_g1_decode_batch);
+}
+inline std::vector<G2> decode_g2_batch(const std::vector<std::string>& w) {
+    return detail::decode<G2, bn_g2, BN_B200_G2_WIRE_BYTES>(w, bn_b200_g2_decode_batch);
+}
+
 }  // namespace bn

@@ -56,6 +56,24 @@ int main(int argc, char** argv) {
             if (pw[i] != want_pow[i]) { fprintf(stderr, "pow_batch mismatch at %zu\n", i); return 1; }
             if (memcmp(&mg[i], &want_g1[i], sizeof(bn::G1))) { fprintf(stderr, "mul_batch mismatch at %zu\n", i); return 1; }
         }
+        // wire format round trip (src/groups/mod.rs:143-205): decode(encode(p)) is the same group element
+        auto w1 = bn::encode_batch(g1);
+        auto w2 = bn::encode_batch(g2);
+        auto d1 = bn::decode_g1_batch(w1);
+        auto d2 = bn::decode_g2_batch(w2);
+        if (bn::encode_batch(d1) != w1 || bn::encode_batch(d2) != w2) { fprintf(stderr, "wire round trip mismatch\n"); return 1; }
+        auto gt2 = bn::pairing_batch(d1, d2);
+        for (size_t i = 0; i < n; i++)
+            if (gt2[i] != want_gt[i]) { fprintf(stderr, "pairing of decoded points mismatch at %zu\n", i); return 1; }
+        bool rejected = false;
+        try {
+            auto bad = w1;
+            bad[0][bad[0].size() - 1] ^= 1;  // y off by one bit: "point is not on the curve"
+            (void)bn::decode_g1_batch(bad);
+        } catch (const bn::DecodeError& e) {
+            rejected = e.index == 0 && (e.status == 3 || e.status == 2);
+        }
+        if (!rejected) { fprintf(stderr, "corrupted record was not rejected\n"); return 1; }
     } catch (const bn::Error& e) {
         fprintf(stderr, "bn::Error %d: %s\n", e.code, e.what());
         return 3;
