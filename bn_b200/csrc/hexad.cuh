@@ -320,26 +320,33 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
 
 // f^u then conjugate (reference exp_by_neg_z, src/fields/fq12.rs:97-101, 229-246).
 // VALID FOR ELEMENTS OF THE CYCLOTOMIC SUBGROUP ONLY (all three uses inside the final exponentiation are):
-// there f^-1 = conj(f), so u is walked in width-3 NAF (digits 0, +-1, +-3): 62 Granger-Scott squarings and
-// 17 + 1 multiplications instead of the reference's 62 + 27.  Gt is canonical, so any addition chain for the same
-// exponent gives the same bytes.
-// Register diet: a and a^3 are only touched on the 18 non-zero digits, so they are PARKED in the lane's private
-// shared-memory slots (c.park / c.unpark, slots HX_PARK_A / HX_PARK_A3) and only the running value stays in registers.
-// On return slot HX_PARK_A still holds a (hx_final_exp re-reads it).
-#define HX_PARK_A 0
-#define HX_PARK_A3 1
-#define HX_PARK_X 2   // two slots for the caller's values that are idle during an exponentiation
-#define HX_PARK_Y 3
-#define HX_PARK_SLOTS 4
+// there f^-1 = conj(f), so u is walked in width-4 NAF (digits 0, +-1, +-3, +-5, +-7): 62 Granger-Scott squarings and
+// 13 + 3 multiplications (+ 1 squaring for a^2) instead of the reference's 62 + 27 (width 3: 17 + 1).  Gt is canonical,
+// so any addition chain for the same exponent gives the same bytes.
+// Register diet: the odd powers a, a^3, a^5, a^7 are only touched on the 14 non-zero digits, so they are PARKED in the
+// lane's private shared-memory slots (c.park / c.unpark, slots HX_PARK_A + 0..3) and only the running value stays in
+// registers.  On return slot HX_PARK_A still holds a (hx_final_exp re-reads it).
+#define HX_PARK_A 0   // a, a^3, a^5, a^7 in slots 0..3
+#define HX_PARK_X 4   // two slots for the caller's values that are idle during an exponentiation
+#define HX_PARK_Y 5
+#define HX_PARK_SLOTS 6
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_exp_by_neg_z(const Ctx c, Fp2 a) {
     c.park(HX_PARK_A, a);
-    c.park(HX_PARK_A3, hx_mul(c, hx_cyc_sqr(c, a), a));
-    Fp2 res = c.unpark(HX_PARK_A);  // leading digit is +1
+    {
+        Fp2 a2 = hx_cyc_sqr(c, a);
+        Fp2 p = a;
+        for (int j = 1; j < 4; j++) {  // a^3, a^5, a^7
+            p = hx_mul(c, p, a2);
+            c.park(HX_PARK_A + j, p);
+        }
+    }
+    Fp2 res = c.unpark(HX_PARK_A + BN_U_WNAF_TOP);  // leading digit
     for (int b = BN_U_WNAF_LEN - 2; b >= 0; b--) {
         res = hx_cyc_sqr(c, res);
         if ((BN_U_WNAF_NZ >> b) & 1ULL) {
-            Fp2 m = c.unpark(((BN_U_WNAF_3 >> b) & 1ULL) ? HX_PARK_A3 : HX_PARK_A);
+            const int idx = (int)((BN_U_WNAF_M0 >> b) & 1ULL) | ((int)((BN_U_WNAF_M1 >> b) & 1ULL) << 1);
+            Fp2 m = c.unpark(HX_PARK_A + idx);
             if ((BN_U_WNAF_NEG >> b) & 1ULL) m = hx_conj(c, m);
             res = hx_mul(c, m, res);
         }

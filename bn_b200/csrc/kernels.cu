@@ -772,7 +772,7 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_
     if (g.profiling) CU(cudaEventRecord(g.ev[1], st));
     const unsigned hb = blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), ht = 32 * HEX_WARPS_PER_BLOCK;
 #if BN_SPLIT_KERNELS
-    k_miller<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.lines, W(d_out), n);
+    k_miller<<<hb, ht, sizeof(HexSmem), st>>>(g.lines, W(d_out), n);  // no parking area: the Miller loop keeps one live value
     if (g.profiling) CU(cudaEventRecord(g.ev[3], st));
     if (d_k)
         k_fexp_pow<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, W(d_k), W(d_out), n);
@@ -782,7 +782,7 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_
 #else
     if (g.profiling) CU(cudaEventRecord(g.ev[3], st));
     if (d_k) {
-        k_miller<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.lines, W(d_out), n);
+        k_miller<<<hb, ht, sizeof(HexSmem), st>>>(g.lines, W(d_out), n);
         k_fexp_pow<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, W(d_k), W(d_out), n);
         g_launches += 1;
     } else {
@@ -832,7 +832,7 @@ int bn_b200_init(int device) {
     if (prop.major < 10) return fail(BN_B200_ENODEV, "device is not sm_100-class; kernels are built for sm_100a only");
     if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CU(cudaFuncSetAttribute(k_miller_fexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HexSmem)));
     CU(cudaFuncSetAttribute(k_fexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_fexp_pow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_miller_fexp, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
