@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "fused", "nccl"],
+                    help="N > 1: fused = results stored by the kernel epilogue into every peer's buffer over NVLink; "
+                         "nccl = all_gather after the kernels; auto = fused when peer memory is available")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -221,10 +224,32 @@ def main():
     del base1, base2
     d_out = torch.empty((n, 48), dtype=torch.int64, device=dev)
     gathered = torch.empty((world * n, 48), dtype=torch.int64, device=dev) if world > 1 else None
+    fused, gather_mode = None, "none"
+    if world > 1:
+        gather_mode = "NCCL all_gather of Gt (384 B/pair)"
+        if args.gather in ("auto", "fused"):
+            try:
+                from bn_b200.dist import FusedGather
+                fused = FusedGather(n, dev)
+                gather_mode = "fused: k_fexp_gather stores each Gt into every peer's buffer over NVLink (symmetric memory) + barrier"
+            except Exception as e:  # noqa: BLE001
+                if args.gather == "fused":
+                    raise
+                if rank == 0:
+                    print("bench.py: fused gather unavailable (%s); using NCCL all_gather" % e, file=sys.stderr)
+        # all ranks must take the same path
+        flag = torch.tensor([1 if fused is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and fused is not None:
+            fused, gather_mode = None, "NCCL all_gather of Gt (384 B/pair)"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step():
         flush.zero_()  # L2 flush between steps (the 535 MB line buffer streamed per step also exceeds L2)
+        if fused is not None:
+            fused.pairing_batch(lib, d_g1, d_g2, sp)
+            fused.barrier()
+            return
         chk(lib.bn_b200_pairing_batch_dev(dptr(d_g1), dptr(d_g2), dptr(d_out), ctypes.c_size_t(n), sp))
         if world > 1:
             dist.all_gather_into_tensor(gathered, d_out)
@@ -253,6 +278,11 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = lib.bn_b200_launch_count() - l0
+    if fused is not None:  # outside the timed region: the fused gather must equal compute + NCCL all_gather, bit for bit
+        chk(lib.bn_b200_pairing_batch_dev(dptr(d_g1), dptr(d_g2), dptr(d_out), ctypes.c_size_t(n), sp))
+        dist.all_gather_into_tensor(gathered, d_out)
+        torch.cuda.synchronize()
+        assert torch.equal(gathered, fused.result()), "fused peer-store gather differs from the NCCL all_gather"
     clocks = sampler.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -405,7 +435,7 @@ def main():
             "vs_baseline": None, "dtype": "u32 limbs (256-bit Montgomery integers)", "data": "synthetic",
             "config": {"workload": "2^14 batched optimal-ate pairings per GPU (BASELINE config 4; N=8 is config 5's 2^17)",
                        "pairs_per_gpu": n, "global_pairs": world * n, "parallelism": "dp%d (independent pairs)" % world,
-                       "gather": "NCCL all_gather of Gt (384 B/pair)" if world > 1 else "none",
+                       "gather": gather_mode,
                        "l2": "256 MiB flush write between steps + %d MB line buffer streamed per step (> 126 MB L2)" % (n * lib.bn_b200_num_lines() * 320 // 1000000),
                        "inputs": "P=G1::one()*a, Q=G2::one()*b, Jacobian z!=1, seeds 0xB2000004+rank"},
             "clocks": clocks,

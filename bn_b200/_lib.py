@@ -7,7 +7,7 @@ SO_PATH = os.environ.get("BN_B200_SO") or os.path.join(_HERE, "libbn_b200.so")  
 
 EXPORTS = [
     "bn_b200_init", "bn_b200_shutdown", "bn_b200_last_error", "bn_b200_sm_count", "bn_b200_num_lines",
-    "bn_b200_pairing_batch", "bn_b200_pairing_batch_dev", "bn_b200_pairing_pow_batch", "bn_b200_pairing_pow_batch_dev",
+    "bn_b200_pairing_batch", "bn_b200_pairing_batch_dev", "bn_b200_pairing_batch_gather_dev", "bn_b200_pairing_pow_batch", "bn_b200_pairing_pow_batch_dev",
     "bn_b200_g1_mul_batch", "bn_b200_g1_mul_batch_dev", "bn_b200_g2_mul_batch", "bn_b200_g2_mul_batch_dev",
     "bn_b200_gt_pow_batch", "bn_b200_gt_pow_batch_dev", "bn_b200_gt_mul_batch", "bn_b200_gt_mul_batch_dev",
     "bn_b200_gt_inv_batch", "bn_b200_gt_inv_batch_dev",

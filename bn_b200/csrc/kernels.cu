@@ -651,6 +651,21 @@ k_fexp_pow(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k, ui
     Fp2 f = fexp_part<true>(h, ld_fp2(p), flags, k);
     if (h.active) st_fp2(p, f);
 }
+// Final exponentiation fused with the multi-GPU gather: the epilogue stores each result straight
+// into every peer's gather buffer over NVLink (peer-mapped memory), at this rank's slot base; no separate all-gather.
+// `out` = this rank's own slot (holds the Miller values written by k_miller).
+#define BN_MAX_PEERS 8
+struct PeerOut {
+    uint32_t* slot[BN_MAX_PEERS];  // slot[r] = peer r's gather buffer + this rank's offset
+};
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, FEXP_MIN_BLOCKS)
+k_fexp_gather(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ out, PeerOut peers, int world, size_t n) {
+    HexIndex h = hex_index_dyn(n);
+    const size_t off = h.pidx * 96 + 16 * gt_slot(h.ctx.kk);
+    Fp2 f = fexp_part<false>(h, ld_fp2(out + off), flags, nullptr);
+    if (h.active)
+        for (int r = 0; r < world; r++) st_fp2(peers.slot[r] + off, f);
+}
 // fused single-kernel form (A/B: BN_SPLIT_KERNELS=0)
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
 k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
@@ -799,6 +814,28 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_
     return 0;
 }
 
+// pairing + fused gather: results go to slot[r] (r < world) of every peer; slot[rank] is also the Miller scratch
+int pairing_gather_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const PeerOut& peers, int world, int rank, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    if (g.lines_cap < n) {
+        if (g.lines) cudaFree(g.lines);
+        g.lines = nullptr;
+        g.lines_cap = 0;
+        cudaError_t e = cudaMalloc(&g.lines, n * (size_t)BN_NUM_LINES * BN_LINE_WORDS * 4 + 4096);
+        if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc(line buffer)", e);
+        g.lines_cap = n;
+    }
+    int rc = ensure_buf(reinterpret_cast<void**>(&g.flags), &g.flags_cap, n);
+    if (rc) return rc;
+    k_pair_lines_duo<<<blocks_for(2 * n, DUO_BLOCK), DUO_BLOCK, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
+    const unsigned hb = blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), ht = 32 * HEX_WARPS_PER_BLOCK;
+    k_miller<<<hb, ht, sizeof(HexSmem), st>>>(g.lines, peers.slot[rank], n);
+    k_fexp_gather<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, peers.slot[rank], peers, world, n);
+    g_launches += 3;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // generic "copy in, run the _dev variant, copy out" driver for the host-pointer entry points
 template <class Launch>
 int host_call(const void* a, size_t a_bytes, const void* b, size_t b_bytes, void* out, size_t out_bytes, Launch launch) {
@@ -835,6 +872,8 @@ int bn_b200_init(int device) {
     CU(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HexSmem)));
     CU(cudaFuncSetAttribute(k_fexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_fexp_pow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_fexp_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_fexp_gather, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_miller_fexp, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_miller, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(k_fexp, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -914,6 +953,21 @@ int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n) 
                      [&](void* a, void* b, void* o, cudaStream_t st) {
                          return pairing_dev_locked((const bn_g1*)a, (const bn_g2*)b, nullptr, (bn_gt*)o, n, st);
                      });
+}
+int bn_b200_pairing_batch_gather_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* const* peer_out, int world, int rank, size_t n,
+                                     void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (world < 1 || world > BN_MAX_PEERS || rank < 0 || rank >= world) return fail(BN_B200_EINVAL, "bad world / rank (1..8 peers)");
+    if (n && (!d_p || !d_q || !peer_out)) return fail(BN_B200_EINVAL, "null pointer");
+    PeerOut po;
+    for (int r = 0; r < BN_MAX_PEERS; r++) po.slot[r] = nullptr;
+    for (int r = 0; r < world; r++) {
+        if (!peer_out[r]) return fail(BN_B200_EINVAL, "null peer buffer");
+        po.slot[r] = W(peer_out[r] + (size_t)rank * n);
+    }
+    return pairing_gather_dev_locked(d_p, d_q, po, world, rank, n, stream ? (cudaStream_t)stream : g.stream);
 }
 int bn_b200_pairing_pow_batch_dev(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, void* stream) {
     std::lock_guard<std::mutex> lk(g_mu);

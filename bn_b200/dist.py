@@ -46,3 +46,46 @@ def pairing_batch_sharded(g1: np.ndarray, g2: np.ndarray, compute=None, device=N
     out = torch.empty((world * per, 48), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(out, buf)
     return out.cpu().numpy().view(np.uint64)[:n]
+
+
+class FusedGather:
+    """Peer-mapped gather buffer for `bn_b200_pairing_batch_gather_dev`: every rank allocates world * n Gt slots in
+    symmetric (peer-accessible) device memory; the final-exponentiation kernel of rank r stores its results straight into
+    slot range [r * n, (r + 1) * n) of EVERY rank's buffer over NVLink, so no separate all-gather runs.
+
+    Uses torch.distributed._symmetric_memory for the allocation / handle exchange and its barrier for the cross-rank
+    ordering; raises if peer access is not available (the caller then keeps the NCCL all-gather)."""
+
+    def __init__(self, n_per_rank: int, device, group=None):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("FusedGather supports up to 8 peers (one NVSwitch domain)")
+        self.n = n_per_rank
+        self.buf = symm_mem.empty((self.world * n_per_rank, 48), dtype=torch.int64, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = list(self.handle.buffer_ptrs)
+        if len(ptrs) != self.world or not all(ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+        self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+
+    def pairing_batch(self, lib, d_g1, d_g2, stream_ptr):
+        """Enqueue lines + Miller + final exponentiation with the fused peer-store epilogue for this rank's n pairs."""
+        import ctypes
+        from . import _lib
+        _lib.check(lib.bn_b200_pairing_batch_gather_dev(ctypes.c_void_p(d_g1.data_ptr()), ctypes.c_void_p(d_g2.data_ptr()),
+                                                        self._ptrs, self.world, self.rank, ctypes.c_size_t(self.n), stream_ptr))
+
+    def barrier(self):
+        """All ranks' kernels up to here have completed and their peer stores are visible."""
+        self.handle.barrier()
+
+    def result(self):
+        return self.buf

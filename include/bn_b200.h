@@ -57,6 +57,14 @@ int bn_b200_num_lines(void);
 int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n);
 int bn_b200_pairing_batch_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t n, void* stream);
 
+/* Multi-GPU form: this rank's n results are stored by the final-exponentiation kernel's epilogue
+ * directly into EVERY rank's gather buffer, peer_out[r][rank * n + i] for r = 0..world-1 (peer-mapped device memory
+ * reachable over NVLink, e.g. a CUDA-IPC / symmetric-memory allocation; peer_out is a HOST array of `world` device
+ * pointers, each to world * n elements).  Replaces pairing_batch_dev + an all-gather of Gt; the caller synchronises the
+ * ranks (barrier) before reading.  world <= 8. */
+int bn_b200_pairing_batch_gather_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* const* peer_out, int world, int rank, size_t n,
+                                     void* stream);
+
 /* out[i] = pairing(p[i], q[i]).pow(k[i]) in one pass (the pattern of reference examples/joux.rs:19-21
  * and test_binlinearity, src/groups/mod.rs:811).  Same bytes as bn_b200_pairing_batch followed by bn_b200_gt_pow_batch. */
 int bn_b200_pairing_pow_batch(const bn_g1* p, const bn_g2* q, const bn_fr* k, bn_gt* out, size_t n);

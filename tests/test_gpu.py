@@ -308,3 +308,27 @@ def test_device_pointer_api_with_torch(bn):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint64), cref.pairing_batch(g1, g2, 8))
     assert lib.bn_b200_launch_count() >= 2
+
+
+@pytest.mark.gpu
+def test_fused_gather_entry_point_single_rank(bn):
+    """bn_b200_pairing_batch_gather_dev with world = 1 (the peer table holds only this device's buffer): same bytes as
+    pairing_batch.  The multi-rank form is exercised by bench.py --gpus N (asserts equality with the NCCL all_gather)."""
+    import ctypes
+    import torch
+    lib = bn.load()
+    g1, g2 = util.synth_pairs(0xB200000A, 37)
+    want = bn.pairing_batch(g1, g2)
+    dev = torch.device("cuda", 0)
+    d1 = torch.from_numpy(g1.view(np.int64)).to(dev)
+    d2 = torch.from_numpy(g2.view(np.int64)).to(dev)
+    out = torch.zeros((len(g1), 48), dtype=torch.int64, device=dev)
+    ptrs = (ctypes.c_void_p * 1)(out.data_ptr())
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        rc = lib.bn_b200_pairing_batch_gather_dev(ctypes.c_void_p(d1.data_ptr()), ctypes.c_void_p(d2.data_ptr()), ptrs, 1, 0,
+                                                  ctypes.c_size_t(len(g1)), ctypes.c_void_p(st.cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
+    assert lib.bn_b200_pairing_batch_gather_dev(None, None, ptrs, 9, 0, ctypes.c_size_t(1), None) != 0  # world > 8 rejected
