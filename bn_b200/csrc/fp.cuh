@@ -481,6 +481,24 @@ BN_HD Fp fp_neg_lazy(const Fp& a) {
     (void)sub8(r.v, p, a.v);
     return r;
 }
+// The modulus held in REGISTERS, loaded from memory so that ptxas cannot fold it back into immediates: p - a then is one
+// IADD3.X per limb (register operands take the ~ modifier); with immediate modulus limbs ptxas spends a LOP3 + IADD3.X
+// per limb.  Worth it when one function negates several values (hx_cyc_sqr: six).
+struct ModRegs {
+    uint32_t p[8];
+};
+template <class M>
+BN_HD ModRegs mod_regs() {  // portable form (immediates); kernels load the limbs from shared memory instead (Ctx::mod_q)
+    ModRegs r;
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) r.p[i] = M::m(i);
+    return r;
+}
+BN_HD Fp fp_neg_lazy_r(const ModRegs& q, const Fp& a) {
+    Fp r;
+    (void)sub8(r.v, q.p, a.v);
+    return r;
+}
 template <class M>
 BN_HD Fp fp_dbl(const Fp& a) {
     return fp_add<M>(a, a);

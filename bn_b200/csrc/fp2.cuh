@@ -213,6 +213,33 @@ BN_HD void fp_small_reduce9(uint32_t* v, uint32_t* out, const KqNone&) {
     for (int i = 0; i < 8; i++) out[i] = v[i];
 }
 
+// ---- lazy 9-limb integers (value < 16q): sums of a few canonical / lazily negated elements, brought back to canonical
+// form by ONE quotient-estimate reduction instead of a conditional correction per addition -------------------------------
+struct Lazy9 {
+    uint32_t v[9];
+};
+BN_HD Lazy9 lazy_add(const Fp& a, const Fp& b) {
+    Lazy9 r;
+    r.v[8] = add8(r.v, a.v, b.v);
+    return r;
+}
+BN_HD void lazy_acc(Lazy9& r, const Fp& a) { r.v[8] += addi8(r.v, a.v); }
+// r = 2*z + t
+BN_HD Lazy9 lazy_dbl_add(const Lazy9& z, const Lazy9& t) {
+    Lazy9 r;
+    r.v[0] = z.v[0] << 1;
+    BN_UNROLL
+    for (int i = 1; i < 9; i++) r.v[i] = (z.v[i] << 1) | (z.v[i - 1] >> 31);
+    r.v[8] += t.v[8] + addi8(r.v, t.v);
+    return r;
+}
+template <class Row>
+BN_HD Fp lazy_reduce(Lazy9 x, const Row& row) {
+    Fp r;
+    fp_small_reduce9(x.v, r.v, row);
+    return r;
+}
+
 // multiply by xi = 9 + i:  (9x - y) + (9y + x) i.   reference src/fields/fq2.rs:70-72 (a full Fq2 mul there)
 template <class Row>
 BN_HD Fp2 fp2_mul_xi_tab(const Fp2& a, const Row& row) {

@@ -22,7 +22,8 @@
 // 512-bit accumulators are live.
 //
 // All functions are collective over the hexad: every lane calls them with its own coefficient.
-// `Ctx` supplies k(), put(slot, value), get(source lane index within the hexad, slot), sync(), mul_xi(Fq2),
+// `Ctx` supplies k(), put(slot, value), get(source lane index within the hexad, slot), get_or_zero(cond, lane, slot),
+// small_reduce(lazy 9-limb integer < 16q), sync(), mul_xi(Fq2),
 // park(slot, value) / unpark(slot) (lane-private storage outside the register file) and
 // inv(Fq element, identical in the six lanes); kernels.cu binds them to shared memory + __syncwarp and a block-wide batched
 // inversion, tests/host_emu binds them to a barrier exchange between six host threads and a Fermat inversion.
@@ -281,6 +282,20 @@ BN_HD Fp2 hx_frob(const Ctx& c, const Fp2& a, int p) {
 // Fq12 = Fq4[w]/(w^3 - s), Fq4 = Fq2[s]/(s^2 - xi), s = w^3: the three Fq4 coefficients are the lane pairs
 // (0,3), (1,4), (2,5).  Each pair is squared with one Fq2 product per lane
 //   (x + y s)^2 = [(x+y)(x + xi y) - xy - xi xy] + [2xy] s .
+// Post-processing of one Fq component: with t = (pre: r - tmp - xo | lane 1: 2 xo | lanes 3,5: 2 r) the output is
+// 3t -+ 2a = 2(t -+ a) + t (statement order of fq12.rs:198-221).  Everything is summed as a lazy 9-limb integer
+// (negations are q - x) and reduced once: T <= 3q, Z = T + (q - a | a) <= 4q, H = 2Z + T <= 11q < 16q.
+template <class Ctx>
+BN_HD Fp hx_cyc_combine(const Ctx& c, const ModRegs& q, bool pre, bool lane1, const Fp& r, const Fp& tmp, const Fp& xo, const Fp& a) {
+    const Fp x1 = fp_select(lane1, xo, r);
+    const Fp x2 = fp_select(pre, fp_neg_lazy_r(q, tmp), x1);
+    const Fp x3 = fp_select(pre, fp_neg_lazy_r(q, xo), fp_zero());
+    Lazy9 t = lazy_add(x1, x2);
+    lazy_acc(t, x3);
+    Lazy9 z = t;
+    lazy_acc(z, fp_select(pre, fp_neg_lazy_r(q, a), a));
+    return c.small_reduce(lazy_dbl_add(z, t));
+}
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     const int k = c.k();
@@ -291,14 +306,16 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     c.put(0, a);
     c.put(1, c.mul_xi(a));
     c.sync();
-    Fp2 x = c.get(lo, 0);
-    Fp2 y = c.get(hi, 0);
-    Fp2 xy = c.get(hi, 1);
-    Fp2 f0, f1;  // factors, components < 2q
-    f0.c0 = fp_add_raw(x.c0, fp_select(pre, y.c0, fp_zero()));
-    f0.c1 = fp_add_raw(x.c1, fp_select(pre, y.c1, fp_zero()));
-    f1.c0 = fp_add_raw(fp_select(pre, xy.c0, y.c0), fp_select(pre, x.c0, fp_zero()));
-    f1.c1 = fp_add_raw(fp_select(pre, xy.c1, y.c1), fp_select(pre, x.c1, fp_zero()));
+    // factors (components < 2q): pre lanes (x + y)(x + xi y), the others x * y; the role picks the ADDRESS it loads
+    // from (a slot or the block's zero slot), so no selects are spent on operands
+    Fp2 f0 = c.get(lo, 0), f1 = c.get(hi, pre ? 1 : 0);
+    {
+        const Fp2 u = c.get_or_zero(pre, hi, 0), v = c.get_or_zero(pre, lo, 0);
+        f0.c0 = fp_add_raw(f0.c0, u.c0);
+        f0.c1 = fp_add_raw(f0.c1, u.c1);
+        f1.c0 = fp_add_raw(f1.c0, v.c0);
+        f1.c1 = fp_add_raw(f1.c1, v.c1);
+    }
     typename AccSel<BN_ACC_CYC>::type acc;
     acck_init(acc);
     mac_fp2(acc, f0, f1);
@@ -307,15 +324,11 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
     c.put(2, r);
     c.sync();
     Fp2 tmp = c.get(nib(0x010503u, k), 2);
-    Fp2 r2 = fp2_add_s(r, r);
-    // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*t5 on lane 1
-    Fp2 xo = c.mul_xi(fp2_select(pre, tmp, r2));
-    Fp2 t_pre = fp2_sub_s(fp2_sub_s(r, tmp), xo);           // t0 / t2 / t4
-    Fp2 t_im = fp2_select(k == 1, xo, r2);                   // t1 / t3 / xi*t5
-    Fp2 t = fp2_select(pre, t_pre, t_im);
-    // pre lanes: 3t - 2z = 2(t - z) + t ; other lanes: 3t + 2z = 2(t + z) + t   (statement order of fq12.rs:198-221)
-    Fp2 z = fp2_add_s(t, fp2_select(pre, fp2_neg(a), a));
-    return fp2_add_s(fp2_add_s(z, z), t);
+    // one xi-multiplication serves both roles: xi*tmp on the "pre" lanes, xi*r on lane 1
+    Fp2 xo = c.mul_xi(fp2_select(pre, tmp, r));
+    // xi*r is complex-valued: component 0 of the output uses component 0 of every term, component 1 likewise
+    const ModRegs q = c.mod_q();
+    return Fp2{hx_cyc_combine(c, q, pre, k == 1, r.c0, tmp.c0, xo.c0, a.c0), hx_cyc_combine(c, q, pre, k == 1, r.c1, tmp.c1, xo.c1, a.c1)};
 }
 
 // f^u then conjugate (reference exp_by_neg_z, src/fields/fq12.rs:97-101, 229-246).

@@ -74,6 +74,7 @@ struct HexSmem {
     Fp pre[HEX_PER_BLOCK];
     alignas(16) uint32_t xch[HEX_WARPS_PER_BLOCK][32 * HEX_LANE_STRIDE];
     alignas(16) uint32_t kq[16 * BN_KQ_STRIDE];  // k*q, k = 0..15 (xi-multiplication reduction rows)
+    alignas(16) uint32_t zero[16];               // an all-zero Fq2: operand "absent" for a lane role, selected by address
 #if BN_LINE_TMA
     LineRing ring[HEX_WARPS_PER_BLOCK];
 #endif
@@ -146,6 +147,7 @@ struct DevCtx {
     uint32_t mine;     // shared address of this lane's exchange slots
     uint32_t hexbase;  // shared address of lane 0 of this hexad
     uint32_t kq;       // shared address of the k*q table
+    uint32_t zero;     // shared address of 64 zero bytes
     uint32_t parkbase; // shared address of this lane's parking area (0: kernel has none); layout [slot][16-byte piece][lane]
     __device__ __forceinline__ int k() const { return kk; }
     __device__ __forceinline__ void park(int s, const Fp2& v) const {
@@ -168,6 +170,15 @@ struct DevCtx {
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ void put(int s, const Fp2& v) const { sts_fp2(mine + s * 64, v); }
     __device__ __forceinline__ Fp2 get(int src, int s) const { return lds_fp2(hexbase + src * (HEX_LANE_STRIDE * 4) + s * 64); }
+    __device__ __forceinline__ Fp2 get_or_zero(bool cond, int src, int s) const {
+        return lds_fp2(cond ? hexbase + src * (HEX_LANE_STRIDE * 4) + s * 64 : zero);
+    }
+    __device__ __forceinline__ Fp small_reduce(const Lazy9& x) const { return lazy_reduce(x, KqRowLds{kq}); }
+    __device__ __forceinline__ ModRegs mod_q() const {  // row 1 of the k*q table
+        ModRegs r;
+        KqRowLds{kq}(1u, r.p);
+        return r;
+    }
     __device__ __forceinline__ Fp inv(const Fp& x) const {
 #if HEX_BATCH_INV
         return block_batch_inv(x, kk == 0 ? slot : -1, slot, HEX_PER_BLOCK, sm->val, sm->pre);
@@ -565,7 +576,10 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int hex = lane / 6;  // 0..5 (5 = the two spare lanes)
-    if (threadIdx.x < 16) kq_table_fill(sm->kq, threadIdx.x);
+    if (threadIdx.x < 16) {
+        kq_table_fill(sm->kq, threadIdx.x);
+        sm->zero[threadIdx.x] = 0;
+    }
     __syncthreads();
     HexIndex h;
     h.ctx.kk = lane - hex * 6;
@@ -575,6 +589,7 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     // the two spare lanes (30, 31) write their own slots but read hexad 4's, so every read stays inside the warp's area
     h.ctx.hexbase = smem_u32(sm->xch[warp] + (hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * 6 * HEX_LANE_STRIDE);
     h.ctx.kq = smem_u32(sm->kq);
+    h.ctx.zero = smem_u32(sm->zero);
     h.ctx.parkbase = 0;
     size_t idx = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP + hex;
     h.active = (hex < HEX_PER_WARP) && (idx < n);

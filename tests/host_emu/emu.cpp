@@ -50,6 +50,15 @@ struct HostCtx {
         (void)init;
         return fp2_mul_xi_t(a, tab);
     }
+    static const uint32_t* kq_tab() {
+        static uint32_t tab[16 * BN_KQ_STRIDE];
+        static bool init = [] { for (int k = 0; k < 16; k++) kq_table_fill(tab, k); return true; }();
+        (void)init;
+        return tab;
+    }
+    ModRegs mod_q() const { return mod_regs<MQ>(); }
+    Fp small_reduce(const Lazy9& x) const { return lazy_reduce(x, KqRowPtr{kq_tab()}); }
+    Fp2 get_or_zero(bool cond, int src, int s) const { return cond ? sh->slot[src][s] : fp2_zero(); }
     void put(int s, const Fp2& v) const { sh->slot[kk][s] = v; }
     Fp2 get(int src, int s) const { return sh->slot[src][s]; }
     void sync() const { sh->bar.wait(); }
