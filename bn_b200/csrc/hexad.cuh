@@ -47,7 +47,7 @@ namespace bn {
 //   AccK3  three carry-save accumulators P0 = sum x0 y0, P1 = sum x1 y1, P2 = sum (x0+x1)(y0+y1); the round loop is
 //          almost pure IMAD.WIDE (one IADD3.X per 4-IMAD chain) and the Karatsuba recombination happens once per
 //          reduction (~64 IADD3 per round + ~160 per operation, 120 accumulator registers)
-// The choice is made per operation (BN_ACC_MUL / _SQR / _LINE / _CYC = 2 or 3).
+// The choice is made per operation (BN_ACC_MUL / _SQR / _LINE / _CYC = 2, 3 or 4 (AccK2S, below)).
 struct AccK2 {
     Wide a0, a1;
 };
@@ -96,6 +96,31 @@ BN_HD void acck_finish(const AccK3& A, Wide& a0, Wide& a1) {
     add16(a0.w, t0.w);
     sub16(a0.w, t1.w);
 }
+// AccK2S: three merged 512-bit sums S0 = sum x0 y0, S1 = sum x1 y1, S2 = sum (x0+x1)(y0+y1) (mod 2^512; S2 may wrap, the
+// recombination below is mod 2^512 too and its true value is in range).  3 x 16 accumulate IADD3 per round instead of
+// AccK2's 5 x 16, one 4 x 16 recombination per operation; pays off from two rounds up (dense product, squaring).
+struct AccK2S {
+    Wide s0, s1, s2;
+};
+BN_HD void acck_init(AccK2S& A) {
+    A.s0 = wide_zero();
+    A.s1 = wide_zero();
+    A.s2 = wide_zero();
+}
+BN_HD void mac_fp2(AccK2S& A, const Fp2& x, const Fp2& y) {
+    wide_mac1(A.s0, x.c0, y.c0);
+    wide_mac1(A.s1, x.c1, y.c1);
+    wide_mac1(A.s2, fp_add_raw(x.c0, x.c1), fp_add_raw(y.c0, y.c1));
+}
+BN_HD void acck_finish(const AccK2S& A, Wide& a0, Wide& a1) {
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) a0.w[i] = WIDE_6Q2_f(i);
+    add16(a0.w, A.s0.w);
+    sub16(a0.w, A.s1.w);
+    a1 = A.s2;
+    sub16(a1.w, A.s0.w);
+    sub16(a1.w, A.s1.w);
+}
 template <int N>
 struct AccSel {
     typedef AccK2 type;
@@ -104,14 +129,20 @@ template <>
 struct AccSel<3> {
     typedef AccK3 type;
 };
+template <>
+struct AccSel<4> {
+    typedef AccK2S type;
+};
+// run 32 (dynamic instructions per call, tools/dyn_counts.py): AccK2S against the previous choice -- dense product 2893
+// vs 3077 (AccK2), squaring 2298 vs 2391 (AccK2), line product 1603 vs 1728 (AccK3; k_miller also drops to 158 registers).
 #ifndef BN_ACC_MUL
-#define BN_ACC_MUL 2
+#define BN_ACC_MUL 4
 #endif
 #ifndef BN_ACC_SQR
-#define BN_ACC_SQR 2
+#define BN_ACC_SQR 4
 #endif
 #ifndef BN_ACC_LINE
-#define BN_ACC_LINE 3   // run 22: 6.84 ms vs 6.93 ms; the same change on the dense product or the squaring loses (7.10-7.12 ms)
+#define BN_ACC_LINE 4
 #endif
 #ifndef BN_ACC_CYC
 #define BN_ACC_CYC 2
