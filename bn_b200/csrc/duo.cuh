@@ -11,7 +11,8 @@
 
 namespace bn {
 
-// Duo context D: h() in {0,1} (which component this lane produces), swap(v) = the partner lane's v.
+// Duo context D: h() in {0,1} (which component this lane produces), swap(v) = the partner lane's v,
+// small_reduce9(v, out) = quotient-estimate reduction of a 9-limb value < 16q (k*q table in shared memory on the device).
 template <class D>
 BN_HD Fp2 duo_join(const D& d, const Fp& mine) {
     Fp other = d.swap(mine);
@@ -65,7 +66,7 @@ BN_HD_NOINLINE Fp2 duo_mul_xi(const D d, Fp2 a) {
     c = addi8(v, addend.v);
     v[8] += c;
     Fp r;
-    fp_small_reduce9(v, r.v, KqNone());
+    d.small_reduce9(v, r.v);
     return duo_join(d, r);
 }
 

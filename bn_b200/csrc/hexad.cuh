@@ -249,8 +249,7 @@ BN_UNROLL_N(BN_SQR_UNROLL)
         // slot: doubled (2) in rounds 0-1 and for sources 3,4 in round 2; plain (0) otherwise in round 2; xi (1) in round 3
         const int xslot = r < 2 ? 2 : (r == 2 ? ((xsrc == 3 || xsrc == 4) ? 2 : 0) : 1);
         Fp2 x = c.get(xsrc, xslot);
-        Fp2 y = c.get(nib(ys, k), 0);
-        y = fp2_select(r == 3 && (k & 1) != 0, fp2_zero(), y);
+        Fp2 y = c.get_or_zero(!(r == 3 && (k & 1) != 0), nib(ys, k), 0);  // odd lanes idle in round 3: zero by address
         mac_fp2(acc, x, y);
     }
     return reduce2(acc);

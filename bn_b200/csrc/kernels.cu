@@ -500,7 +500,9 @@ __global__ void __launch_bounds__(64) k_pair_lines(const uint32_t* __restrict__ 
 // K4a, lane-pair form (duo.cuh): lanes (2j, 2j+1) compute the lines of one pairing, one Fq2 output component each.
 struct DevDuo {
     int hh;
+    uint32_t kq;  // shared address of the k*q table
     __device__ __forceinline__ int h() const { return hh; }
+    __device__ __forceinline__ void small_reduce9(uint32_t* v, uint32_t* out) const { fp_small_reduce9(v, out, KqRowLds{kq}); }
     __device__ __forceinline__ Fp swap(const Fp& v) const {
         Fp r;
 #pragma unroll
@@ -545,7 +547,10 @@ __global__ void __launch_bounds__(DUO_BLOCK) k_pair_lines_duo(const uint32_t* __
     Q.x = ld_fp2(g2 + i * 48);
     Q.y = ld_fp2(g2 + i * 48 + 16);
     Q.z = ld_fp2(g2 + i * 48 + 32);
-    DuoX<DevDuo> X_{DevDuo{(int)(t & 1)}};
+    __shared__ alignas(16) uint32_t s_kq[16 * BN_KQ_STRIDE];  // k*q rows for the xi-multiplication's reduction
+    if (threadIdx.x < 16) kq_table_fill(s_kq, threadIdx.x);
+    __syncthreads();
+    DuoX<DevDuo> X_{DevDuo{(int)(t & 1), smem_u32(s_kq)}};
     Fp px, py;
     Fp2 qx, qy;
     __shared__ Fp s_val[DUO_BLOCK / 2], s_pre[DUO_BLOCK / 2];  // one slot per pairing of the block

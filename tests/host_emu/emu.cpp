@@ -74,6 +74,12 @@ struct HostDuo {
     int hh;
     HostDuoShared* sh;
     int h() const { return hh; }
+    void small_reduce9(uint32_t* v, uint32_t* out) const {
+        static uint32_t tab[16 * BN_KQ_STRIDE];
+        static bool init = [] { for (int k = 0; k < 16; k++) kq_table_fill(tab, k); return true; }();
+        (void)init;
+        fp_small_reduce9(v, out, KqRowPtr{tab});
+    }
     Fp swap(const Fp& v) const {
         sh->slot[hh] = v;
         sh->bar.wait();
