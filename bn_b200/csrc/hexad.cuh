@@ -1,16 +1,16 @@
-// hexad.cuh -- Fq12 / Gt arithmetic spread over SIX lanes of a warp ("hexad"), registers only.
+// hexad.cuh -- Fq12 / Gt arithmetic spread over SIX lanes of a warp ("hexad"), live values in registers.
 //
 // Representation.  The reference's tower Fq12 = Fq6[w]/(w^2 - v), Fq6 = Fq2[v]/(v^3 - xi)
 // (src/fields/fq12.rs:26-31, src/fields/fq6.rs:42-48) is the same ring as Fq2[w]/(w^6 - xi):
 //     c0.c0 + c1.c0 w + c0.c1 w^2 + c1.c1 w^3 + c0.c2 w^4 + c1.c2 w^5 .
 // Lane k of a hexad (k = lane % 6; five hexads per warp, lanes 30/31 idle) holds the Fq2 coefficient g_k
-// of w^k of EVERY live Fq12 value, so a whole Gt costs 16 registers per lane and the final exponentiation's
-// half-dozen live values stay in the register file: no shared-memory or local-memory round trips for state.
+// of w^k of EVERY live Fq12 value, so a whole Gt costs 16 registers per lane; values that stay idle for a whole
+// exponentiation are parked in lane-private shared memory (c.park / c.unpark), everything else is in registers.
 //
 // Multiplication is the length-6 negacyclic-style convolution
 //     c_k = sum_{i+j=k} a_i b_j + xi * sum_{i+j=k+6} a_i b_j
-// evaluated one Fq2 product per lane per step; operands travel between lanes with warp shuffles, the sender
-// choosing between a_i and xi*a_i, and the products of a lane are summed as 512-bit integers and reduced once
+// evaluated one Fq2 product per lane per step; operands travel between lanes through shared-memory slots (below),
+// and the products of a lane are summed as 512-bit integers and reduced once
 // (2 Montgomery reductions per lane per Fq12 operation).  Results are canonical, hence bit-identical to the
 // reference's Karatsuba tower (src/fields/fq12.rs:275-307, src/fields/fq6.rs:113-158) which computes the same
 // ring element.

@@ -6,11 +6,14 @@
 //   k_pair_lines_duo  K4a to_affine (one inversion per pair, batched per block) + the ate line schedule (88 lines, NAF
 //                         walk of 6u+2), one LANE PAIR per pairing, streamed to HBM in consumption order
 //                         (k_pair_lines: the one-thread-per-pairing form, kept for A/B via BN_B200_LINES=solo)
-//   k_miller_fexp     K4b Miller accumulation + final exponentiation, one 6-lane hexad per pairing (5 per warp); Fq12
-//                         state in registers, operands exchanged through shared-memory slots, lines prefetched by TMA
-//   k_miller_fexp_pow     same + fused Gt::pow (row f-1)
+//   k_miller          K4b Miller accumulation, one 6-lane hexad per pairing (5 per warp, 3 blocks/SM); Fq12 state in
+//                         registers, operands exchanged through shared-memory slots (LDS/STS by 32-bit shared address),
+//                         line coefficients read from a TMA-fed ring; writes the unreduced Miller value to the output
+//   k_fexp            K4c final exponentiation in place on that buffer (2 blocks/SM; idle values parked in shared memory)
+//   k_fexp_gather         same, the epilogue stores each result into every peer GPU's gather buffer over NVLink (row e)
+//   k_fexp_pow            same + fused Gt::pow (row f-1);  k_miller_fexp: the fused single-kernel form (BN_SPLIT_KERNELS=0)
 //   k_gt_mul/k_gt_pow/k_gt_inv K5 batched Gt arithmetic on hexads
-//   k_fr_op, k_g1_normalize, k_g2_normalize   rows f-4 / f-3
+//   k_fr_op, k_g{1,2}_{normalize,check,encode,decode}, k_fr_{encode,decode}   rows f-4 / f-3 (wire.cuh)
 // There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include <cuda_runtime.h>
 
