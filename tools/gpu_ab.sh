@@ -18,15 +18,12 @@ v=sys.argv[1]
 try:
     d=json.loads(open('gpurun_out/bench_%s.log'%v).read().strip().splitlines()[-1])
     r=d['roofline']
-    print(v,'value %.0f e2e %.0f ms/step %.3f lines %.3f ms miller %.3f ms imad_peak %.2f T frac %.3f whole %.3f fqmul %.3e (%.2f) clocks %s'%(d['value'],d['e2e']['value'],d['ms_per_step'],r['kernel_ms']['k_pair_lines'],r['kernel_ms']['k_miller_fexp'],r['peak'],r['frac'],r['whole_path_frac'],r['fq_mul_chain']['fq_mul_per_s'],r['fq_mul_chain']['imad_frac'],d['clocks']))
+    print(v,'value %.0f e2e %.0f ms/step %.3f lines %.3f ms miller %.3f ms fexp %.3f ms imad_peak %.2f T frac %.3f whole %.3f fqmul %.3e (%.2f) clocks %s'%(d['value'],d['e2e']['value'],d['ms_per_step'],r['kernel_ms']['k_pair_lines'],r['kernel_ms']['k_miller'],r['kernel_ms']['k_fexp'],r['peak'],r['frac'],r['whole_path_frac'],r['fq_mul_chain']['fq_mul_per_s'],r['fq_mul_chain']['imad_frac'],d['clocks']))
 except Exception as e:
     print(v,'FAILED',e); print(open('gpurun_out/bench_%s.err'%v).read()[-1500:])
 PY
 done
 unset BN_B200_SO BN_B200_LINES
 if [ "$2" = "ncu" ]; then
-  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:k_miller_fexp -s 2 -c 1 -o gpurun_out/prof_miller python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_miller.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:k_pair_lines -s 2 -c 1 -o gpurun_out/prof_lines python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_lines.log 2>&1
-  ls -la gpurun_out/
+  tools/gpu_ncu.sh ab   # launch list of one bench step + one --set full capture of k_pair_lines_duo, k_miller, k_fexp
 fi
