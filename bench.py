@@ -441,7 +441,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": n * BYTES_IN,
                     "d2h_bytes_per_step": n * BYTES_OUT,
-                    "path": "bn_b200_pairing_batch (host pointers, pinned): H2D + 3 kernels + D2H per step"},
+                    "path": "bn_b200_pairing_batch (host pointers, pinned): H2D + 3 kernels per step, results stored by the last "
+                            "kernel's epilogue directly into the pinned output buffer (zero-copy D2H)"},
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "int-imad", "kernel": dominant,

@@ -747,6 +747,7 @@ struct State {
     size_t stage_cap[3] = {0, 0, 0};
     bool profiling = false;
     bool lines_duo = true;  // line kernel mapping: lane pair per pairing (default) or one thread per pairing
+    bool zero_copy_out = true;  // host-pointer pairing_batch: write results directly into a pinned output buffer
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before lines | before Miller | after the last kernel | before final exp
     bool ev_valid = false;
     cudaStream_t ev_stream = nullptr;
@@ -837,8 +838,8 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_
     return 0;
 }
 
-// pairing + fused gather: results go to slot[r] (r < world) of every peer; slot[rank] is also the Miller scratch
-int pairing_gather_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const PeerOut& peers, int world, int rank, size_t n, cudaStream_t st) {
+// pairing + fused gather: results go to slot[r] (r < world) of every peer; `scratch` (n Gt) holds the Miller values
+int pairing_gather_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const PeerOut& peers, int world, uint32_t* scratch, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
     if (g.lines_cap < n) {
         if (g.lines) cudaFree(g.lines);
@@ -852,8 +853,8 @@ int pairing_gather_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const PeerOut&
     if (rc) return rc;
     k_pair_lines_duo<<<blocks_for(2 * n, DUO_BLOCK), DUO_BLOCK, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
     const unsigned hb = blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), ht = 32 * HEX_WARPS_PER_BLOCK;
-    k_miller<<<hb, ht, sizeof(HexSmem), st>>>(g.lines, peers.slot[rank], n);
-    k_fexp_gather<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, peers.slot[rank], peers, world, n);
+    k_miller<<<hb, ht, sizeof(HexSmem), st>>>(g.lines, scratch, n);
+    k_fexp_gather<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, scratch, peers, world, n);
     g_launches += 3;
     CU(cudaGetLastError());
     return 0;
@@ -903,6 +904,7 @@ int bn_b200_init(int device) {
     for (int i = 0; i < 4; i++)
         if (!g.ev[i]) CU(cudaEventCreate(&g.ev[i]));
     if (const char* e = getenv("BN_B200_LINES")) g.lines_duo = strcmp(e, "solo") != 0;  // A/B switch, both are bit-exact
+    if (const char* e = getenv("BN_B200_ZEROCOPY")) g.zero_copy_out = strcmp(e, "0") != 0;  // A/B switch
     g.device = device;
     g.sm_count = prop.multiProcessorCount;
     g.ready = true;
@@ -972,6 +974,26 @@ int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n) 
     if (rc) return rc;
     if (n == 0) return 0;
     if (!p || !q || !out) return fail(BN_B200_EINVAL, "null pointer");
+    // Page-locked, device-mapped output buffer (cudaHostAlloc / cudaHostRegister): the final-exponentiation epilogue
+    // stores the results straight into it over PCIe while the other blocks are still computing -- no D2H pass.
+    if (g.zero_copy_out) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            if ((rc = ensure_buf(&g.stage[0], &g.stage_cap[0], n * sizeof(bn_g1)))) return rc;
+            if ((rc = ensure_buf(&g.stage[1], &g.stage_cap[1], n * sizeof(bn_g2)))) return rc;
+            if ((rc = ensure_buf(&g.stage[2], &g.stage_cap[2], n * sizeof(bn_gt)))) return rc;
+            CU(cudaMemcpyAsync(g.stage[0], p, n * sizeof(bn_g1), cudaMemcpyHostToDevice, g.stream));
+            CU(cudaMemcpyAsync(g.stage[1], q, n * sizeof(bn_g2), cudaMemcpyHostToDevice, g.stream));
+            PeerOut po;
+            for (int r = 0; r < BN_MAX_PEERS; r++) po.slot[r] = nullptr;
+            po.slot[0] = W(at.devicePointer);
+            if ((rc = pairing_gather_dev_locked((const bn_g1*)g.stage[0], (const bn_g2*)g.stage[1], po, 1, W(g.stage[2]), n, g.stream)))
+                return rc;
+            CU(cudaStreamSynchronize(g.stream));
+            return 0;
+        }
+        (void)cudaGetLastError();  // pageable memory: not an error, take the staged path
+    }
     return host_call(p, n * sizeof(bn_g1), q, n * sizeof(bn_g2), out, n * sizeof(bn_gt),
                      [&](void* a, void* b, void* o, cudaStream_t st) {
                          return pairing_dev_locked((const bn_g1*)a, (const bn_g2*)b, nullptr, (bn_gt*)o, n, st);
@@ -990,7 +1012,7 @@ int bn_b200_pairing_batch_gather_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* 
         if (!peer_out[r]) return fail(BN_B200_EINVAL, "null peer buffer");
         po.slot[r] = W(peer_out[r] + (size_t)rank * n);
     }
-    return pairing_gather_dev_locked(d_p, d_q, po, world, rank, n, stream ? (cudaStream_t)stream : g.stream);
+    return pairing_gather_dev_locked(d_p, d_q, po, world, po.slot[rank], n, stream ? (cudaStream_t)stream : g.stream);
 }
 int bn_b200_pairing_pow_batch_dev(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, void* stream) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -14,7 +14,8 @@
  *   - return 0 on success, a negative BN_B200_E* code on failure; never unwinds, never aborts;
  *     bn_b200_last_error() gives a message for the last failure on the calling thread.
  *   - caller owns every buffer; the library owns its stream, scratch memory and events.
- *   - host-pointer entry points copy H2D, run the kernels and copy D2H before returning.
+ *   - host-pointer entry points copy H2D, run the kernels and copy D2H before returning (bn_b200_pairing_batch writes
+ *     a page-locked, device-mapped `out` buffer directly from the last kernel instead of a D2H pass).
  *   - *_dev entry points take DEVICE pointers (same layouts) and enqueue on `stream`
  *     (a cudaStream_t cast to void*; NULL = the library's own stream) without synchronising.
  *   - thread-safe: calls are serialised by an internal lock (the crate's types are Send + Sync,

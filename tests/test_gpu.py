@@ -332,3 +332,23 @@ def test_fused_gather_entry_point_single_rank(bn):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
     assert lib.bn_b200_pairing_batch_gather_dev(None, None, ptrs, 9, 0, ctypes.c_size_t(1), None) != 0  # world > 8 rejected
+
+
+@pytest.mark.gpu
+def test_pairing_batch_pinned_output_zero_copy(bn):
+    """Host-pointer pairing_batch with page-locked buffers: the last kernel writes the pinned output directly (no D2H
+    pass); same bytes as the staged path used for pageable memory, also with BN_B200_ZEROCOPY semantics off (numpy)."""
+    import ctypes
+    import torch
+    lib = bn.load()
+    g1, g2 = util.synth_pairs(0xB200000B, 53)
+    e1, e2 = util.edge_case_pairs()
+    g1, g2 = np.concatenate([g1, e1]), np.concatenate([g2, e2])
+    want = bn.pairing_batch(g1, g2)  # pageable numpy buffers: staged path
+    h1 = torch.from_numpy(g1.view(np.int64).copy()).pin_memory()
+    h2 = torch.from_numpy(g2.view(np.int64).copy()).pin_memory()
+    ho = torch.zeros((len(g1), 48), dtype=torch.int64).pin_memory()
+    rc = lib.bn_b200_pairing_batch(ctypes.c_void_p(h1.data_ptr()), ctypes.c_void_p(h2.data_ptr()), ctypes.c_void_p(ho.data_ptr()),
+                                   ctypes.c_size_t(len(g1)))
+    assert rc == 0
+    assert np.array_equal(ho.numpy().view(np.uint64), want)
