@@ -352,3 +352,24 @@ def test_pairing_batch_pinned_output_zero_copy(bn):
                                    ctypes.c_size_t(len(g1)))
     assert rc == 0
     assert np.array_equal(ho.numpy().view(np.uint64), want)
+
+
+@pytest.mark.gpu
+def test_gt_mul_pow_extreme_coefficients(bn):
+    """The kernels' lazy arithmetic at its bounds: Gt images whose coefficients are all q-1 / 0 / mixed (not pairing
+    values: Gt mul and pow are plain Fq12 operations, reference src/lib.rs:171-179) against the big-int oracle."""
+    import random
+    rng = random.Random(6)
+    qm1 = o.Q - 1
+    pats = [[qm1] * 12, [0] * 12, [1] + [0] * 11, [qm1, 0] * 6, [0, qm1] * 6, [qm1] * 6 + [0] * 6,
+            [rng.choice((0, 1, qm1, qm1 - 1, o.Q // 2)) for _ in range(12)], [rng.randrange(o.Q) for _ in range(12)]]
+    elems = [o.fq12_from_flat(p) for p in pats]
+    a = np.stack([util.gt_img(x) for x in elems])
+    b = np.roll(a, 3, axis=0)
+    got = bn.gt_mul_batch(a, b)
+    for i in range(len(elems)):
+        assert np.array_equal(got[i], util.gt_img(o.fq12_mul(elems[i], elems[(i - 3) % len(elems)]))), i
+    k = np.stack([util.fr_img(5)] * len(elems))
+    got = bn.gt_pow_batch(a, k)
+    for i in range(len(elems)):
+        assert np.array_equal(got[i], util.gt_img(o.fq12_pow(elems[i], 5))), i

@@ -173,3 +173,21 @@ def test_pairing_edge_cases():
     egt = cref.pairing_batch(e1, e2)
     for i in range(len(e1)):
         assert np.array_equal(emu.pairing(e1[i], e2[i]), egt[i]), i
+
+
+def test_hexad_ops_extreme_coefficients():
+    """Bound checks of the lazy arithmetic (512-bit sums that wrap, lazy 9-limb post-processing): all-(q-1), all-zero,
+    identity and mixed coefficient patterns through the dense product, the squaring and the Granger-Scott squaring
+    (a polynomial map: the reference evaluates it on non-cyclotomic inputs too, src/fields/mod.rs:171-201)."""
+    import random
+    rng = random.Random(5)
+    qm1 = o.Q - 1
+    pats = [[qm1] * 12, [0] * 12, [1] + [0] * 11, [qm1, 0] * 6, [0, qm1] * 6, [qm1] * 6 + [0] * 6,
+            [rng.choice((0, 1, qm1, qm1 - 1, o.Q // 2)) for _ in range(12)], [rng.randrange(o.Q) for _ in range(12)]]
+    elems = [o.fq12_from_flat(p) for p in pats]
+    for i, x in enumerate(elems):
+        xi = util.gt_img(x)
+        assert np.array_equal(emu.gt_op(2, xi), util.gt_img(o.fq12_cyclotomic_squared(x))), ("cyc", i)
+        assert np.array_equal(emu.gt_op(1, xi), util.gt_img(o.fq12_sqr(x))), ("sqr", i)
+        y = elems[(i + 3) % len(elems)]
+        assert np.array_equal(emu.gt_op(0, xi, util.gt_img(y)), util.gt_img(o.fq12_mul(x, y))), ("mul", i)
