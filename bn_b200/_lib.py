@@ -18,7 +18,7 @@ EXPORTS = [
     "bn_b200_fr_encode_batch", "bn_b200_fr_encode_batch_dev", "bn_b200_g1_decode_batch", "bn_b200_g1_decode_batch_dev",
     "bn_b200_g2_decode_batch", "bn_b200_g2_decode_batch_dev", "bn_b200_fr_decode_batch", "bn_b200_fr_decode_batch_dev",
     "bn_b200_fq_mul_chain", "bn_b200_fq_mul_chain_dev", "bn_b200_imad_peak_dev",
-    "bn_b200_set_profiling", "bn_b200_last_pairing_kernel_ms", "bn_b200_last_pairing_kernel_ms3", "bn_b200_launch_count",
+    "bn_b200_set_max_chunk", "bn_b200_set_profiling", "bn_b200_last_pairing_kernel_ms", "bn_b200_last_pairing_kernel_ms3", "bn_b200_launch_count",
 ]
 
 

@@ -748,6 +748,7 @@ struct State {
     bool profiling = false;
     bool lines_duo = true;  // line kernel mapping: lane pair per pairing (default) or one thread per pairing
     bool zero_copy_out = true;  // host-pointer pairing_batch: write results directly into a pinned output buffer
+    size_t chunk = (size_t)1 << 18;  // pairings per pass over the line buffer
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before lines | before Miller | after the last kernel | before final exp
     bool ev_valid = false;
     cudaStream_t ev_stream = nullptr;
@@ -790,7 +791,7 @@ inline unsigned blocks_for(size_t n, unsigned per_block) { return (unsigned)((n 
 inline const uint32_t* W(const void* p) { return reinterpret_cast<const uint32_t*>(p); }
 inline uint32_t* W(void* p) { return reinterpret_cast<uint32_t*>(p); }
 
-int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, cudaStream_t st) {
+int pairing_dev_chunk(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
     if (g.lines_cap < n) {
         if (g.lines) cudaFree(g.lines);
@@ -839,7 +840,7 @@ int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_
 }
 
 // pairing + fused gather: results go to slot[r] (r < world) of every peer; `scratch` (n Gt) holds the Miller values
-int pairing_gather_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const PeerOut& peers, int world, uint32_t* scratch, size_t n, cudaStream_t st) {
+int pairing_gather_dev_chunk(const bn_g1* d_p, const bn_g2* d_q, const PeerOut& peers, int world, uint32_t* scratch, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
     if (g.lines_cap < n) {
         if (g.lines) cudaFree(g.lines);
@@ -857,6 +858,28 @@ int pairing_gather_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const PeerOut&
     k_fexp_gather<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, scratch, peers, world, n);
     g_launches += 3;
     CU(cudaGetLastError());
+    return 0;
+}
+
+// Batches larger than g.chunk pairings are processed in chunks on the same stream, so the library-owned line buffer
+// (28 160 B per pairing) stays bounded: 2^18 pairings = 7.4 GB whatever the batch size.  (With profiling enabled the
+// recorded kernel times are those of the last chunk.)
+int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, cudaStream_t st) {
+    for (size_t off = 0; off < n; off += g.chunk) {
+        const size_t m = n - off < g.chunk ? n - off : g.chunk;
+        int rc = pairing_dev_chunk(d_p + off, d_q + off, d_k ? d_k + off : nullptr, d_out + off, m, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+int pairing_gather_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const PeerOut& peers, int world, uint32_t* scratch, size_t n, cudaStream_t st) {
+    for (size_t off = 0; off < n; off += g.chunk) {
+        const size_t m = n - off < g.chunk ? n - off : g.chunk;
+        PeerOut po = peers;
+        for (int r = 0; r < world; r++) po.slot[r] = peers.slot[r] + off * 96;
+        int rc = pairing_gather_dev_chunk(d_p + off, d_q + off, po, world, scratch + off * 96, m, st);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -931,6 +954,11 @@ int bn_b200_sm_count(void) { return g.sm_count; }
 int bn_b200_num_lines(void) { return BN_NUM_LINES; }
 unsigned long long bn_b200_launch_count(void) { return g_launches.load(); }
 
+int bn_b200_set_max_chunk(size_t pairs) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g.chunk = pairs ? pairs : ((size_t)1 << 18);
+    return 0;
+}
 int bn_b200_set_profiling(int enable) {
     std::lock_guard<std::mutex> lk(g_mu);
     g.profiling = enable != 0;

@@ -145,6 +145,10 @@ int bn_b200_fq_mul_chain_dev(const uint64_t* d_a, const uint64_t* d_b, uint64_t*
  * IMAD.WIDE.U32 (the instruction every Fq product is made of).  d_scratch: >= 4 bytes of device memory. */
 int bn_b200_imad_peak_dev(uint32_t* d_scratch, uint32_t blocks, uint32_t iters, void* stream);
 
+/* Pairing batches larger than `pairs` are processed in chunks of that many pairings so that the library-owned line buffer
+ * (28 160 B per pairing) stays bounded; default 2^18 (7.4 GB), 0 restores the default. */
+int bn_b200_set_max_chunk(size_t pairs);
+
 /* Per-kernel device timing of the most recent pairing_batch[_dev] call, measured with CUDA events on the
  * stream the kernels were launched on (enable first; reading synchronises that stream).
  * ms[0] = line-schedule kernel, ms[1] = Miller-loop + final-exponentiation kernels (two launches since run 28). */

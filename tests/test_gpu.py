@@ -373,3 +373,28 @@ def test_gt_mul_pow_extreme_coefficients(bn):
     got = bn.gt_pow_batch(a, k)
     for i in range(len(elems)):
         assert np.array_equal(got[i], util.gt_img(o.fq12_pow(elems[i], 5))), i
+
+
+@pytest.mark.gpu
+def test_pairing_chunked_batches(bn):
+    """Batches above the chunk size are processed in several passes over the bounded line buffer: identical results,
+    through the device-resident, the staged host and the pinned zero-copy paths."""
+    import ctypes
+    import torch
+    lib = bn.load()
+    g1, g2 = util.synth_pairs(0xB200000C, 64)
+    g1, g2 = np.tile(g1, (4, 1))[:237], np.tile(g2, (4, 1))[:237]
+    want = bn.pairing_batch(g1, g2)
+    assert lib.bn_b200_set_max_chunk(ctypes.c_size_t(100)) == 0
+    try:
+        assert np.array_equal(bn.pairing_batch(g1, g2), want)          # 100 + 100 + 37
+        h1 = torch.from_numpy(g1.view(np.int64).copy()).pin_memory()
+        h2 = torch.from_numpy(g2.view(np.int64).copy()).pin_memory()
+        ho = torch.zeros((len(g1), 48), dtype=torch.int64).pin_memory()
+        assert lib.bn_b200_pairing_batch(ctypes.c_void_p(h1.data_ptr()), ctypes.c_void_p(h2.data_ptr()),
+                                         ctypes.c_void_p(ho.data_ptr()), ctypes.c_size_t(len(g1))) == 0
+        assert np.array_equal(ho.numpy().view(np.uint64), want)
+        k = util.synth_scalars(0xB200000D, len(g1))
+        assert np.array_equal(bn.pairing_pow_batch(g1, g2, k), bn.gt_pow_batch(want, k))
+    finally:
+        lib.bn_b200_set_max_chunk(ctypes.c_size_t(0))
