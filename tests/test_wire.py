@@ -207,3 +207,29 @@ def test_gpu_fr_wire(bn):
     ok = st == 0
     assert np.array_equal(imgs[ok], np.stack([util.fr_img(v) for v in vals if v < o.R_ORDER]))
     assert np.array_equal(api.encode_batch("fr", imgs[ok]), recs[ok])
+
+
+def test_emu_wire_decode_fuzz():
+    """Random mutations of valid records and fully random records: status and decoded value must agree with the big-int
+    oracle's decode (the reference's checks in the reference's order)."""
+    rng = np.random.default_rng(20261017)
+    for kind, limit, rounds in (("g1", 6, 60), ("g2", 3, 14), ("fr", 4, 60)):
+        good = _cases(kind, limit)
+        for it in range(rounds):
+            rec = good[it % len(good)].copy()
+            mode = it % 4
+            if mode == 0:
+                rec[int(rng.integers(0, len(rec)))] ^= np.uint8(1 << int(rng.integers(0, 8)))   # one flipped bit
+            elif mode == 1:
+                rec[1 if kind != "fr" else 0] = np.uint8(rng.integers(0x30, 0x100))              # a large leading coordinate byte
+            elif mode == 2:
+                rec[:] = rng.integers(0, 256, len(rec), dtype=np.uint8)                          # noise
+                if kind != "fr" and it % 8 == 2:
+                    rec[0] = 4
+            img, st = emu.wire_decode(kind, rec)
+            assert st == _oracle_status(kind, rec), (kind, it, bytes(rec).hex())
+            if st == 0 and kind == "fr":
+                assert np.array_equal(img, util.fr_img(int.from_bytes(bytes(rec), "big")))
+            elif st == 0 and rec[0] == 4:
+                dec, F, to = (o.decode_g1, o.FQ, util.img_g1) if kind == "g1" else (o.decode_g2, o.FQ2, util.img_g2)
+                assert o.g_eq(F, to(img), dec(bytes(rec)))
