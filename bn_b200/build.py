@@ -18,6 +18,17 @@ def sources():
         os.path.join(os.path.dirname(HERE), "include", "bn_b200.h")]
 
 
+def source_hash() -> str:
+    """sha256 over the kernel sources: ties a committed ncu artefact (profiles/ncu_kernels.json) to the build it profiled."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cu", ".cuh", ".inc")):
+            with open(os.path.join(CSRC, f), "rb") as fh:
+                h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
 def is_stale() -> bool:
     if not os.path.exists(SO):
         return True

@@ -98,6 +98,25 @@ BN_HD_NOINLINE Jac<F> jac_add(const Jac<F>& p, const Jac<F>& o) {
     return out;
 }
 
+// reference src/groups/mod.rs:314-327: zero is returned unchanged, otherwise (x, -y, z)
+template <class F>
+BN_HD Jac<F> jac_neg(const Jac<F>& p) {
+    Jac<F> r = p;
+    if (!F::is_zero(p.z)) r.y = F::neg(p.y);
+    return r;
+}
+
+// projective equality, reference src/groups/mod.rs:83-109
+template <class F>
+BN_HD bool jac_eq(const Jac<F>& p, const Jac<F>& o) {
+    typedef typename F::T T;
+    if (F::is_zero(p.z)) return F::is_zero(o.z);
+    if (F::is_zero(o.z)) return false;
+    T zz1 = F::sqr(p.z), zz2 = F::sqr(o.z);
+    if (!F::eq(F::mul(p.x, zz2), F::mul(o.x, zz1))) return false;
+    return F::eq(F::mul(p.y, F::mul(o.z, zz2)), F::mul(o.y, F::mul(p.z, zz1)));
+}
+
 // `G * Fr`: reference src/groups/mod.rs:250-270.  fr is the Montgomery image of the scalar (as stored in bn::Fr).
 template <class F>
 BN_HD Jac<F> jac_mul(const Jac<F>& p, const Fp& fr) {

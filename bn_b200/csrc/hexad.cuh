@@ -397,6 +397,24 @@ BN_HD_NOINLINE Fp2 hx_exp_by_neg_z(const Ctx c, Fp2 a) {
     return hx_conj(c, res);
 }
 
+// exp_by_neg_z exactly as the reference evaluates it (src/fields/fq12.rs:97-101, 229-246): MSB-first binary walk of u that
+// skips the squarings before the first set bit, literal Granger-Scott squaring, `self * res`, then conjugation.  Unlike
+// hx_exp_by_neg_z above it makes no use of f^-1 = conj(f), so it matches the reference on inputs OUTSIDE the cyclotomic
+// subgroup too (the reference's test_cyclotomic_exp vector, src/fields/mod.rs:171-201, is one).
+template <class Ctx>
+BN_HD Fp2 hx_exp_by_neg_z_literal(const Ctx& c, const Fp2& a) {
+    Fp2 res = hx_one(c);
+    bool found_one = false;
+    for (int b = 63; b >= 0; b--) {
+        if (found_one) res = hx_cyc_sqr(c, res);
+        if ((BN_U_PARAM >> b) & 1ULL) {
+            found_one = true;
+            res = hx_mul(c, a, res);
+        }
+    }
+    return hx_conj(c, res);
+}
+
 // 1/f for f != 0.  reference src/fields/fq12.rs:284-292 -> fq6.rs:129-141 -> fq2.rs:125-136.
 // f^-1 = conj(f) * N^-1 with N = f * conj(f) in Fq6; the small Fq6/Fq2/Fq inversion chain is done
 // redundantly by every lane (it is a handful of Fq2 products next to one Fq inversion).

@@ -17,12 +17,16 @@
 // There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/bn_b200.h"
 #include "pairing.cuh"
@@ -41,11 +45,21 @@ __device__ __forceinline__ Fp ld_fp(const uint32_t* p) {
     r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
     return r;
 }
+// plain ld.global (coherent): for buffers the same kernel also writes in place (the read-only path of __ldg is undefined there)
+__device__ __forceinline__ Fp ld_fp_rw(const uint32_t* p) {
+    const uint4 a = reinterpret_cast<const uint4*>(p)[0];
+    const uint4 b = reinterpret_cast<const uint4*>(p)[1];
+    Fp r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
 __device__ __forceinline__ void st_fp(uint32_t* p, const Fp& a) {
     reinterpret_cast<uint4*>(p)[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
     reinterpret_cast<uint4*>(p)[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
 }
 __device__ __forceinline__ Fp2 ld_fp2(const uint32_t* p) { return Fp2{ld_fp(p), ld_fp(p + 8)}; }
+__device__ __forceinline__ Fp2 ld_fp2_rw(const uint32_t* p) { return Fp2{ld_fp_rw(p), ld_fp_rw(p + 8)}; }
 __device__ __forceinline__ void st_fp2(uint32_t* p, const Fp2& a) {
     st_fp(p, a.c0);
     st_fp(p + 8, a.c1);
@@ -207,7 +221,10 @@ struct DevLineSrc {
 #if BN_LINE_TMA
 // Line source fed by the TMA engine: one elected lane per warp issues a 1600-byte cp.async.bulk for Miller step t+2
 // as soon as the warp has consumed step t; completion is tracked by an mbarrier transaction count, consumers spin on
-// mbarrier.try_wait.parity (bounded, then trap: a protocol bug must fail the launch, not hang the GPU).
+// mbarrier.try_wait.parity.  A wait that exceeds its polling budget sets bit 0 of the library's device error word (the host
+// turns it into BN_B200_ECUDA after the call) and the warp carries on with whatever the buffer holds: a protocol bug or a
+// stalled copy engine fails THAT call with an error code; it neither hangs the GPU nor poisons the CUDA context (a __trap
+// would).  BN_RING_TRAP=1 restores the trap for debugging.
 struct DevLineSrcTma {
     const uint32_t* gbase;  // lines + p0 * 80 words (row 0 of this warp's five pairings)
     size_t row_words;       // n * 80
@@ -215,6 +232,7 @@ struct DevLineSrcTma {
     uint32_t lane_off;      // byte offset of this lane's hexad inside a ring buffer
     uint32_t coef_off;      // see coef()
     int lane;
+    uint32_t* err;          // device error word (bit 0: line-ring wait timed out)
     __device__ __forceinline__ uint32_t bar(int b) const { return ring + 2 * HEX_LINE_BYTES + 8 * b; }
     __device__ __forceinline__ uint32_t buf(int b) const { return ring + b * HEX_LINE_BYTES; }
     __device__ __forceinline__ void init() const {
@@ -241,13 +259,20 @@ struct DevLineSrcTma {
     __device__ __forceinline__ Handle acquire(int t) const {
         const uint32_t parity = (uint32_t)(t >> 1) & 1u;
         uint32_t ok = 0;
-        for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
+        for (int spin = 0; spin < (1 << 24) && !ok; spin++) {
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                          : "=r"(ok)
                          : "r"(bar(t & 1)), "r"(parity)
                          : "memory");
+            if (spin > (1 << 20)) __nanosleep(128);  // long wait: back off (about 2 s in total before giving up)
         }
-        if (!ok) __trap();
+        if (!ok) {
+#if defined(BN_RING_TRAP) && BN_RING_TRAP
+            __trap();
+#else
+            if (lane == 0) atomicOr(err, 1u);
+#endif
+        }
         return buf(t & 1) + lane_off;
     }
     // coef_off: byte offsets of l0 | l3k | l4k for this lane, packed 10 bits each
@@ -282,6 +307,16 @@ __global__ void __launch_bounds__(256) k_fq_mul_chain(const uint32_t* __restrict
     Fp x = ld_fp(a + i * 8), y = ld_fp(b + i * 8);
 #pragma unroll 2
     for (uint32_t k = 0; k < iters; k++) x = fp_mul<ModQ>(x, y);
+    st_fp(out + i * 8, x);
+}
+
+// Dedicated Montgomery squaring chain x <- x^2 (108 IMAD.WIDE against 136 for a general product; fp_sqr in fp.cuh).
+__global__ void __launch_bounds__(256) k_fq_sqr_chain(const uint32_t* __restrict__ a, uint32_t* __restrict__ out, size_t n, uint32_t iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x = ld_fp(a + i * 8);
+#pragma unroll 2
+    for (uint32_t k = 0; k < iters; k++) x = fp_sqr<ModQ>(x);
     st_fp(out + i * 8, x);
 }
 
@@ -340,6 +375,74 @@ __global__ void __launch_bounds__(128) k_g2_mul(const uint32_t* __restrict__ p, 
     st_fp2(out + i * 48, r.x);
     st_fp2(out + i * 48 + 16, r.y);
     st_fp2(out + i * 48 + 32, r.z);
+}
+
+// ---- row a11: the group law at the boundary (reference impl Add / Sub / Neg for G1, G2: src/lib.rs:97-114, 140-157 ->
+// src/groups/mod.rs:272-347; double: :228-247; PartialEq: :83-109).  One thread per element; outputs are the same
+// un-normalised Jacobian triples the crate produces.  op: 0 a + b, 1 a - b, 2 -a, 3 a.double()
+template <class F>
+struct JacIO;
+template <>
+struct JacIO<FqOps> {
+    static constexpr int WORDS = 24;
+    static __device__ __forceinline__ Jac<FqOps> ld(const uint32_t* p) { return Jac<FqOps>{ld_fp(p), ld_fp(p + 8), ld_fp(p + 16)}; }
+    static __device__ __forceinline__ void st(uint32_t* p, const Jac<FqOps>& a) { st_fp(p, a.x); st_fp(p + 8, a.y); st_fp(p + 16, a.z); }
+};
+template <>
+struct JacIO<Fq2Ops> {
+    static constexpr int WORDS = 48;
+    static __device__ __forceinline__ Jac<Fq2Ops> ld(const uint32_t* p) { return Jac<Fq2Ops>{ld_fp2(p), ld_fp2(p + 16), ld_fp2(p + 32)}; }
+    static __device__ __forceinline__ void st(uint32_t* p, const Jac<Fq2Ops>& a) { st_fp2(p, a.x); st_fp2(p + 16, a.y); st_fp2(p + 32, a.z); }
+};
+template <class F>
+__device__ __forceinline__ void group_op(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typedef JacIO<F> IO;
+    Jac<F> x = IO::ld(a + i * IO::WORDS), r;
+    switch (op) {
+        case 0: r = jac_add<F>(x, IO::ld(b + i * IO::WORDS)); break;
+        case 1: r = jac_add<F>(x, jac_neg<F>(IO::ld(b + i * IO::WORDS))); break;
+        case 2: r = jac_neg<F>(x); break;
+        default: r = jac_double<F>(x); break;
+    }
+    IO::st(out + i * IO::WORDS, r);
+}
+__global__ void __launch_bounds__(128) k_g1_op(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n, int op) {
+    group_op<FqOps>(a, b, out, n, op);
+}
+__global__ void __launch_bounds__(128) k_g2_op(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n, int op) {
+    group_op<Fq2Ops>(a, b, out, n, op);
+}
+__global__ void __launch_bounds__(128) k_g1_eq(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint8_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = jac_eq<FqOps>(JacIO<FqOps>::ld(a + i * 24), JacIO<FqOps>::ld(b + i * 24)) ? 1 : 0;
+}
+__global__ void __launch_bounds__(128) k_g2_eq(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint8_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = jac_eq<Fq2Ops>(JacIO<Fq2Ops>::ld(a + i * 48), JacIO<Fq2Ops>::ld(b + i * 48)) ? 1 : 0;
+}
+
+// Fr::pow(self, exp: Fr) (reference src/lib.rs:24 -> FieldElement::pow, src/fields/mod.rs:35-46: the exponent is
+// U256::from(exp), all 256 bits walked MSB first, squaring from the first iteration).
+__global__ void __launch_bounds__(128) k_fr_pow(const uint32_t* __restrict__ a, const uint32_t* __restrict__ e, uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fp x = ld_fp(a + i * 8);
+    const Fp k = fp_from_mont<ModR>(ld_fp(e + i * 8));
+    Fp r;
+#pragma unroll
+    for (int l = 0; l < 8; l++) r.v[l] = FR_ONE_f(l);
+    for (int w = 7; w >= 0; w--) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int l = 0; l < 8; l++) bits = (w == l) ? k.v[l] : bits;
+        for (int b = 31; b >= 0; b--) {
+            r = fp_sqr<ModR>(r);
+            if ((bits >> b) & 1u) r = fp_mul<ModR>(x, r);
+        }
+    }
+    st_fp(out + i * 8, r);
 }
 
 // ---- rows f-3 / f-4: batched Fr arithmetic and Group::normalize ------------------------------------------------
@@ -626,7 +729,7 @@ __device__ __forceinline__ HexIndex hex_index_dyn(size_t n) {
     h.ctx.parkbase = smem_u32(hex_dyn_smem + sizeof(HexSmem)) + (threadIdx.x >> 5) * HEX_PARK_WARP_BYTES + (threadIdx.x & 31) * 16;
     return h;
 }
-__device__ __forceinline__ Fp2 miller_part(const HexIndex& h, const uint32_t* __restrict__ lines, size_t n) {
+__device__ __forceinline__ Fp2 miller_part(const HexIndex& h, const uint32_t* __restrict__ lines, size_t n, uint32_t* err) {
 #if BN_LINE_TMA
     HexSmem* smem = reinterpret_cast<HexSmem*>(hex_dyn_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -637,7 +740,7 @@ __device__ __forceinline__ Fp2 miller_part(const HexIndex& h, const uint32_t* __
                       (uint32_t)((hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * BN_LINE_WORDS * 4),
                       (uint32_t)(4 * BN_LINE_OFF_L0) | ((uint32_t)(4 * (h.ctx.kk < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3)) << 10) |
                           ((uint32_t)(4 * (h.ctx.kk < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4)) << 20),
-                      lane};
+                      lane, err};
     src.init();
 #else
     DevLineSrc src{lines, n, h.pidx, h.ctx.kk};
@@ -655,23 +758,23 @@ __device__ __forceinline__ Fp2 fexp_part(const HexIndex& h, Fp2 f, const uint8_t
     return f;
 }
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, MILLER_MIN_BLOCKS)
-k_miller(const uint32_t* __restrict__ lines, uint32_t* __restrict__ out, size_t n) {
+k_miller(const uint32_t* __restrict__ lines, uint32_t* __restrict__ out, size_t n, uint32_t* err) {
     HexIndex h = hex_index_dyn(n);
-    Fp2 f = miller_part(h, lines, n);
+    Fp2 f = miller_part(h, lines, n, err);
     if (h.active) st_fp2(out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk), f);
 }
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, FEXP_MIN_BLOCKS)
-k_fexp(const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
+k_fexp(const uint8_t* __restrict__ flags, uint32_t* out, size_t n) {
     HexIndex h = hex_index_dyn(n);
     uint32_t* p = out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk);
-    Fp2 f = fexp_part<false>(h, ld_fp2(p), flags, nullptr);
+    Fp2 f = fexp_part<false>(h, ld_fp2_rw(p), flags, nullptr);
     if (h.active) st_fp2(p, f);
 }
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS_POW)
-k_fexp_pow(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
+k_fexp_pow(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k, uint32_t* out, size_t n) {
     HexIndex h = hex_index_dyn(n);
     uint32_t* p = out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk);
-    Fp2 f = fexp_part<true>(h, ld_fp2(p), flags, k);
+    Fp2 f = fexp_part<true>(h, ld_fp2_rw(p), flags, k);
     if (h.active) st_fp2(p, f);
 }
 // Final exponentiation fused with the multi-GPU gather: the epilogue stores each result straight
@@ -682,18 +785,18 @@ struct PeerOut {
     uint32_t* slot[BN_MAX_PEERS];  // slot[r] = peer r's gather buffer + this rank's offset
 };
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, FEXP_MIN_BLOCKS)
-k_fexp_gather(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ out, PeerOut peers, int world, size_t n) {
+k_fexp_gather(const uint8_t* __restrict__ flags, const uint32_t* out, PeerOut peers, int world, size_t n) {
     HexIndex h = hex_index_dyn(n);
-    const size_t off = h.pidx * 96 + 16 * gt_slot(h.ctx.kk);
-    Fp2 f = fexp_part<false>(h, ld_fp2(out + off), flags, nullptr);
+    const size_t off = h.pidx * 96 + 16 * gt_slot(h.ctx.kk);  // `out` may alias peers.slot[rank]: coherent loads, no __restrict__
+    Fp2 f = fexp_part<false>(h, ld_fp2_rw(out + off), flags, nullptr);
     if (h.active)
         for (int r = 0; r < world; r++) st_fp2(peers.slot[r] + off, f);
 }
 // fused single-kernel form (A/B: BN_SPLIT_KERNELS=0)
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
-k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n) {
+k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n, uint32_t* err) {
     HexIndex h = hex_index_dyn(n);
-    Fp2 f = fexp_part<false>(h, miller_part(h, lines, n), flags, nullptr);
+    Fp2 f = fexp_part<false>(h, miller_part(h, lines, n, err), flags, nullptr);
     if (h.active) st_fp2(out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk), f);
 }
 
@@ -718,6 +821,19 @@ k_gt_inv(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_
     if (h.active) st_fp2(out + h.pidx * 96 + slot, r);
 }
 
+// Fq12::exp_by_neg_z as the reference evaluates it (src/fields/fq12.rs:97-101, 229-246): binary cyclotomic_pow(u) with the
+// literal Granger-Scott squaring, then conjugation -- defined for ANY Fq12 input (a polynomial map), which is what the
+// reference's test_cyclotomic_exp pins (src/fields/mod.rs:171-201, a non-cyclotomic input).  b is unused.
+__global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
+k_gt_exp_neg_z(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n) {
+    __shared__ HexSmem smem;
+    HexIndex h = hex_index(n, &smem);
+    const int slot = 16 * gt_slot(h.ctx.kk);
+    Fp2 x = ld_fp2(a + h.pidx * 96 + slot);
+    Fp2 r = hx_exp_by_neg_z_literal(h.ctx, x);
+    if (h.active) st_fp2(out + h.pidx * 96 + slot, r);
+}
+
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
 k_gt_pow(const uint32_t* __restrict__ a, const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
     __shared__ HexSmem smem;
@@ -729,566 +845,4 @@ k_gt_pow(const uint32_t* __restrict__ a, const uint32_t* __restrict__ k, uint32_
     if (h.active) st_fp2(out + h.pidx * 96 + slot, r);
 }
 
-// ------------------------------------------------------------------------------------------------
-// host side: state, error handling, C ABI
-// ------------------------------------------------------------------------------------------------
-namespace {
-
-struct State {
-    bool ready = false;
-    int device = -1;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    uint32_t* lines = nullptr;
-    size_t lines_cap = 0;  // pairings
-    uint8_t* flags = nullptr;
-    size_t flags_cap = 0;
-    void* stage[3] = {nullptr, nullptr, nullptr};
-    size_t stage_cap[3] = {0, 0, 0};
-    bool profiling = false;
-    bool lines_duo = true;  // line kernel mapping: lane pair per pairing (default) or one thread per pairing
-    bool zero_copy_out = true;  // host-pointer pairing_batch: write results directly into a pinned output buffer
-    size_t chunk = (size_t)1 << 18;  // pairings per pass over the line buffer
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // before lines | before Miller | after the last kernel | before final exp
-    bool ev_valid = false;
-    cudaStream_t ev_stream = nullptr;
-};
-State g;
-std::mutex g_mu;
-std::atomic<unsigned long long> g_launches{0};
-thread_local std::string t_err;
-
-int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
-    char buf[512];
-    if (e != cudaSuccess)
-        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
-    else
-        snprintf(buf, sizeof buf, "%s", what);
-    t_err = buf;
-    return code;
-}
-#define CU(call)                                                        \
-    do {                                                                \
-        cudaError_t e_ = (call);                                        \
-        if (e_ != cudaSuccess) return fail(BN_B200_ECUDA, #call, e_);   \
-    } while (0)
-
-int ensure_ready() {
-    if (g.ready) return 0;
-    return fail(BN_B200_ENODEV, "bn_b200_init() has not succeeded (no CUDA device bound; there is no CPU fallback)");
-}
-int ensure_buf(void** p, size_t* cap, size_t bytes) {
-    if (*cap >= bytes) return 0;
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-    *cap = 0;
-    cudaError_t e = cudaMalloc(p, bytes);
-    if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc", e);
-    *cap = bytes;
-    return 0;
-}
-inline unsigned blocks_for(size_t n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
-inline const uint32_t* W(const void* p) { return reinterpret_cast<const uint32_t*>(p); }
-inline uint32_t* W(void* p) { return reinterpret_cast<uint32_t*>(p); }
-
-int pairing_dev_chunk(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, cudaStream_t st) {
-    if (n == 0) return 0;
-    if (g.lines_cap < n) {
-        if (g.lines) cudaFree(g.lines);
-        g.lines = nullptr;
-        g.lines_cap = 0;
-        cudaError_t e = cudaMalloc(&g.lines, n * (size_t)BN_NUM_LINES * BN_LINE_WORDS * 4 + 4096);  // + slack: the TMA prefetch of a
-                                                                                                    // partly filled last warp reads 5 pairings
-        if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc(line buffer)", e);
-        g.lines_cap = n;
-    }
-    int rc = ensure_buf(reinterpret_cast<void**>(&g.flags), &g.flags_cap, n);
-    if (rc) return rc;
-    if (g.profiling) CU(cudaEventRecord(g.ev[0], st));
-    if (g.lines_duo)
-        k_pair_lines_duo<<<blocks_for(2 * n, DUO_BLOCK), DUO_BLOCK, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
-    else
-        k_pair_lines<<<blocks_for(n, 64), 64, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
-    if (g.profiling) CU(cudaEventRecord(g.ev[1], st));
-    const unsigned hb = blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), ht = 32 * HEX_WARPS_PER_BLOCK;
-#if BN_SPLIT_KERNELS
-    k_miller<<<hb, ht, sizeof(HexSmem), st>>>(g.lines, W(d_out), n);  // no parking area: the Miller loop keeps one live value
-    if (g.profiling) CU(cudaEventRecord(g.ev[3], st));
-    if (d_k)
-        k_fexp_pow<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, W(d_k), W(d_out), n);
-    else
-        k_fexp<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, W(d_out), n);
-    g_launches += 1;
-#else
-    if (g.profiling) CU(cudaEventRecord(g.ev[3], st));
-    if (d_k) {
-        k_miller<<<hb, ht, sizeof(HexSmem), st>>>(g.lines, W(d_out), n);
-        k_fexp_pow<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, W(d_k), W(d_out), n);
-        g_launches += 1;
-    } else {
-        k_miller_fexp<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.lines, g.flags, W(d_out), n);
-    }
-#endif
-    if (g.profiling) {
-        CU(cudaEventRecord(g.ev[2], st));
-        g.ev_valid = true;
-        g.ev_stream = st;
-    }
-    g_launches += 2;
-    CU(cudaGetLastError());
-    return 0;
-}
-
-// pairing + fused gather: results go to slot[r] (r < world) of every peer; `scratch` (n Gt) holds the Miller values
-int pairing_gather_dev_chunk(const bn_g1* d_p, const bn_g2* d_q, const PeerOut& peers, int world, uint32_t* scratch, size_t n, cudaStream_t st) {
-    if (n == 0) return 0;
-    if (g.lines_cap < n) {
-        if (g.lines) cudaFree(g.lines);
-        g.lines = nullptr;
-        g.lines_cap = 0;
-        cudaError_t e = cudaMalloc(&g.lines, n * (size_t)BN_NUM_LINES * BN_LINE_WORDS * 4 + 4096);
-        if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc(line buffer)", e);
-        g.lines_cap = n;
-    }
-    int rc = ensure_buf(reinterpret_cast<void**>(&g.flags), &g.flags_cap, n);
-    if (rc) return rc;
-    k_pair_lines_duo<<<blocks_for(2 * n, DUO_BLOCK), DUO_BLOCK, 0, st>>>(W(d_p), W(d_q), g.lines, g.flags, n);
-    const unsigned hb = blocks_for(n, HEX_WARPS_PER_BLOCK * HEX_PER_WARP), ht = 32 * HEX_WARPS_PER_BLOCK;
-    k_miller<<<hb, ht, sizeof(HexSmem), st>>>(g.lines, scratch, n);
-    k_fexp_gather<<<hb, ht, HEX_DYN_SMEM_BYTES, st>>>(g.flags, scratch, peers, world, n);
-    g_launches += 3;
-    CU(cudaGetLastError());
-    return 0;
-}
-
-// Batches larger than g.chunk pairings are processed in chunks on the same stream, so the library-owned line buffer
-// (28 160 B per pairing) stays bounded: 2^18 pairings = 7.4 GB whatever the batch size.  (With profiling enabled the
-// recorded kernel times are those of the last chunk.)
-int pairing_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, cudaStream_t st) {
-    for (size_t off = 0; off < n; off += g.chunk) {
-        const size_t m = n - off < g.chunk ? n - off : g.chunk;
-        int rc = pairing_dev_chunk(d_p + off, d_q + off, d_k ? d_k + off : nullptr, d_out + off, m, st);
-        if (rc) return rc;
-    }
-    return 0;
-}
-int pairing_gather_dev_locked(const bn_g1* d_p, const bn_g2* d_q, const PeerOut& peers, int world, uint32_t* scratch, size_t n, cudaStream_t st) {
-    for (size_t off = 0; off < n; off += g.chunk) {
-        const size_t m = n - off < g.chunk ? n - off : g.chunk;
-        PeerOut po = peers;
-        for (int r = 0; r < world; r++) po.slot[r] = peers.slot[r] + off * 96;
-        int rc = pairing_gather_dev_chunk(d_p + off, d_q + off, po, world, scratch + off * 96, m, st);
-        if (rc) return rc;
-    }
-    return 0;
-}
-
-// generic "copy in, run the _dev variant, copy out" driver for the host-pointer entry points
-template <class Launch>
-int host_call(const void* a, size_t a_bytes, const void* b, size_t b_bytes, void* out, size_t out_bytes, Launch launch) {
-    int rc;
-    if ((rc = ensure_buf(&g.stage[0], &g.stage_cap[0], a_bytes))) return rc;
-    if ((rc = ensure_buf(&g.stage[1], &g.stage_cap[1], b_bytes))) return rc;
-    if ((rc = ensure_buf(&g.stage[2], &g.stage_cap[2], out_bytes))) return rc;
-    CU(cudaMemcpyAsync(g.stage[0], a, a_bytes, cudaMemcpyHostToDevice, g.stream));
-    CU(cudaMemcpyAsync(g.stage[1], b, b_bytes, cudaMemcpyHostToDevice, g.stream));
-    if ((rc = launch(g.stage[0], g.stage[1], g.stage[2], g.stream))) return rc;
-    CU(cudaMemcpyAsync(out, g.stage[2], out_bytes, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
-    return 0;
-}
-
-}  // namespace
-
-extern "C" {
-
-int bn_b200_init(int device) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g.ready && g.device == device) return 0;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return fail(BN_B200_ENODEV, "no CUDA device visible (this library has no CPU fallback)", e);
-    if (device < 0 || device >= count) return fail(BN_B200_EINVAL, "device index out of range");
-    CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail(BN_B200_ENODEV, "device is not sm_100-class; kernels are built for sm_100a only");
-    if (!g.stream) CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    CU(cudaFuncSetAttribute(k_miller_fexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HexSmem)));
-    CU(cudaFuncSetAttribute(k_fexp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(k_fexp_pow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(k_fexp_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEX_DYN_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(k_fexp_gather, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(k_miller_fexp, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(k_miller, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(k_fexp, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    for (int i = 0; i < 4; i++)
-        if (!g.ev[i]) CU(cudaEventCreate(&g.ev[i]));
-    if (const char* e = getenv("BN_B200_LINES")) g.lines_duo = strcmp(e, "solo") != 0;  // A/B switch, both are bit-exact
-    if (const char* e = getenv("BN_B200_ZEROCOPY")) g.zero_copy_out = strcmp(e, "0") != 0;  // A/B switch
-    g.device = device;
-    g.sm_count = prop.multiProcessorCount;
-    g.ready = true;
-    return 0;
-}
-
-int bn_b200_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!g.ready) return 0;
-    cudaStreamSynchronize(g.stream);
-    if (g.lines) cudaFree(g.lines);
-    if (g.flags) cudaFree(g.flags);
-    for (int i = 0; i < 3; i++)
-        if (g.stage[i]) cudaFree(g.stage[i]);
-    for (int i = 0; i < 4; i++)
-        if (g.ev[i]) cudaEventDestroy(g.ev[i]);
-    cudaStreamDestroy(g.stream);
-    g = State();
-    return 0;
-}
-
-const char* bn_b200_last_error(void) { return t_err.c_str(); }
-int bn_b200_sm_count(void) { return g.sm_count; }
-int bn_b200_num_lines(void) { return BN_NUM_LINES; }
-unsigned long long bn_b200_launch_count(void) { return g_launches.load(); }
-
-int bn_b200_set_max_chunk(size_t pairs) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g.chunk = pairs ? pairs : ((size_t)1 << 18);
-    return 0;
-}
-int bn_b200_set_profiling(int enable) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g.profiling = enable != 0;
-    g.ev_valid = false;
-    return 0;
-}
-int bn_b200_last_pairing_kernel_ms(float ms[2]) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (!ms) return fail(BN_B200_EINVAL, "null output");
-    if (!g.ev_valid) return fail(BN_B200_EINVAL, "no profiled pairing call recorded (call bn_b200_set_profiling(1) first)");
-    CU(cudaEventSynchronize(g.ev[2]));
-    CU(cudaEventElapsedTime(&ms[0], g.ev[0], g.ev[1]));
-    CU(cudaEventElapsedTime(&ms[1], g.ev[1], g.ev[2]));
-    return 0;
-}
-int bn_b200_last_pairing_kernel_ms3(float ms[3]) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (!ms) return fail(BN_B200_EINVAL, "null output");
-    if (!g.ev_valid) return fail(BN_B200_EINVAL, "no profiled pairing call recorded (call bn_b200_set_profiling(1) first)");
-    CU(cudaEventSynchronize(g.ev[2]));
-    CU(cudaEventElapsedTime(&ms[0], g.ev[0], g.ev[1]));
-    CU(cudaEventElapsedTime(&ms[1], g.ev[1], g.ev[3]));
-    CU(cudaEventElapsedTime(&ms[2], g.ev[3], g.ev[2]));
-    return 0;
-}
-
-int bn_b200_pairing_batch_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* d_out, size_t n, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (n && (!d_p || !d_q || !d_out)) return fail(BN_B200_EINVAL, "null pointer");
-    return pairing_dev_locked(d_p, d_q, nullptr, d_out, n, stream ? (cudaStream_t)stream : g.stream);
-}
-int bn_b200_pairing_batch(const bn_g1* p, const bn_g2* q, bn_gt* out, size_t n) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (n == 0) return 0;
-    if (!p || !q || !out) return fail(BN_B200_EINVAL, "null pointer");
-    // Page-locked, device-mapped output buffer (cudaHostAlloc / cudaHostRegister): the final-exponentiation epilogue
-    // stores the results straight into it over PCIe while the other blocks are still computing -- no D2H pass.
-    if (g.zero_copy_out) {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-            if ((rc = ensure_buf(&g.stage[0], &g.stage_cap[0], n * sizeof(bn_g1)))) return rc;
-            if ((rc = ensure_buf(&g.stage[1], &g.stage_cap[1], n * sizeof(bn_g2)))) return rc;
-            if ((rc = ensure_buf(&g.stage[2], &g.stage_cap[2], n * sizeof(bn_gt)))) return rc;
-            CU(cudaMemcpyAsync(g.stage[0], p, n * sizeof(bn_g1), cudaMemcpyHostToDevice, g.stream));
-            CU(cudaMemcpyAsync(g.stage[1], q, n * sizeof(bn_g2), cudaMemcpyHostToDevice, g.stream));
-            PeerOut po;
-            for (int r = 0; r < BN_MAX_PEERS; r++) po.slot[r] = nullptr;
-            po.slot[0] = W(at.devicePointer);
-            if ((rc = pairing_gather_dev_locked((const bn_g1*)g.stage[0], (const bn_g2*)g.stage[1], po, 1, W(g.stage[2]), n, g.stream)))
-                return rc;
-            CU(cudaStreamSynchronize(g.stream));
-            return 0;
-        }
-        (void)cudaGetLastError();  // pageable memory: not an error, take the staged path
-    }
-    return host_call(p, n * sizeof(bn_g1), q, n * sizeof(bn_g2), out, n * sizeof(bn_gt),
-                     [&](void* a, void* b, void* o, cudaStream_t st) {
-                         return pairing_dev_locked((const bn_g1*)a, (const bn_g2*)b, nullptr, (bn_gt*)o, n, st);
-                     });
-}
-int bn_b200_pairing_batch_gather_dev(const bn_g1* d_p, const bn_g2* d_q, bn_gt* const* peer_out, int world, int rank, size_t n,
-                                     void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (world < 1 || world > BN_MAX_PEERS || rank < 0 || rank >= world) return fail(BN_B200_EINVAL, "bad world / rank (1..8 peers)");
-    if (n && (!d_p || !d_q || !peer_out)) return fail(BN_B200_EINVAL, "null pointer");
-    PeerOut po;
-    for (int r = 0; r < BN_MAX_PEERS; r++) po.slot[r] = nullptr;
-    for (int r = 0; r < world; r++) {
-        if (!peer_out[r]) return fail(BN_B200_EINVAL, "null peer buffer");
-        po.slot[r] = W(peer_out[r] + (size_t)rank * n);
-    }
-    return pairing_gather_dev_locked(d_p, d_q, po, world, po.slot[rank], n, stream ? (cudaStream_t)stream : g.stream);
-}
-int bn_b200_pairing_pow_batch_dev(const bn_g1* d_p, const bn_g2* d_q, const bn_fr* d_k, bn_gt* d_out, size_t n, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (n && (!d_p || !d_q || !d_k || !d_out)) return fail(BN_B200_EINVAL, "null pointer");
-    return pairing_dev_locked(d_p, d_q, d_k, d_out, n, stream ? (cudaStream_t)stream : g.stream);
-}
-int bn_b200_pairing_pow_batch(const bn_g1* p, const bn_g2* q, const bn_fr* k, bn_gt* out, size_t n) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (n == 0) return 0;
-    if (!p || !q || !k || !out) return fail(BN_B200_EINVAL, "null pointer");
-    void* d_k = nullptr;
-    cudaError_t e = cudaMalloc(&d_k, n * sizeof(bn_fr));
-    if (e != cudaSuccess) return fail(BN_B200_ENOMEM, "cudaMalloc(scalars)", e);
-    e = cudaMemcpyAsync(d_k, k, n * sizeof(bn_fr), cudaMemcpyHostToDevice, g.stream);
-    if (e != cudaSuccess) { cudaFree(d_k); return fail(BN_B200_ECUDA, "cudaMemcpyAsync(scalars)", e); }
-    rc = host_call(p, n * sizeof(bn_g1), q, n * sizeof(bn_g2), out, n * sizeof(bn_gt),
-                   [&](void* a, void* b, void* o, cudaStream_t st) {
-                       return pairing_dev_locked((const bn_g1*)a, (const bn_g2*)b, (const bn_fr*)d_k, (bn_gt*)o, n, st);
-                   });
-    cudaFree(d_k);
-    return rc;
-}
-
-#define DEFINE_BINARY(NAME, KERNEL, TA, TB, TO, PER_BLOCK, THREADS)                                              \
-    static int NAME##_launch(const void* a, const void* b, void* o, size_t n, cudaStream_t st) {                  \
-        if (n == 0) return 0;                                                                                     \
-        KERNEL<<<blocks_for(n, PER_BLOCK), THREADS, 0, st>>>(W(a), W(b), W(o), n);                                \
-        g_launches += 1;                                                                                          \
-        CU(cudaGetLastError());                                                                                   \
-        return 0;                                                                                                 \
-    }                                                                                                             \
-    int bn_b200_##NAME##_batch_dev(const TA* d_a, const TB* d_b, TO* d_out, size_t n, void* stream) {             \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                     \
-        int rc = ensure_ready();                                                                                  \
-        if (rc) return rc;                                                                                        \
-        if (n && (!d_a || !d_b || !d_out)) return fail(BN_B200_EINVAL, "null pointer");                           \
-        return NAME##_launch(d_a, d_b, d_out, n, stream ? (cudaStream_t)stream : g.stream);                       \
-    }                                                                                                             \
-    int bn_b200_##NAME##_batch(const TA* a, const TB* b, TO* out, size_t n) {                                     \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                     \
-        int rc = ensure_ready();                                                                                  \
-        if (rc) return rc;                                                                                        \
-        if (n == 0) return 0;                                                                                     \
-        if (!a || !b || !out) return fail(BN_B200_EINVAL, "null pointer");                                        \
-        return host_call(a, n * sizeof(TA), b, n * sizeof(TB), out, n * sizeof(TO),                               \
-                         [&](void* x, void* y, void* o, cudaStream_t st) { return NAME##_launch(x, y, o, n, st); }); \
-    }
-
-DEFINE_BINARY(g1_mul, k_g1_mul, bn_g1, bn_fr, bn_g1, 128, 128)
-DEFINE_BINARY(g2_mul, k_g2_mul, bn_g2, bn_fr, bn_g2, 128, 128)
-DEFINE_BINARY(gt_pow, k_gt_pow, bn_gt, bn_fr, bn_gt, HEX_WARPS_PER_BLOCK* HEX_PER_WARP, 32 * HEX_WARPS_PER_BLOCK)
-DEFINE_BINARY(gt_mul, k_gt_mul, bn_gt, bn_gt, bn_gt, HEX_WARPS_PER_BLOCK* HEX_PER_WARP, 32 * HEX_WARPS_PER_BLOCK)
-DEFINE_BINARY(gt_inv2, k_gt_inv, bn_gt, bn_gt, bn_gt, HEX_WARPS_PER_BLOCK* HEX_PER_WARP, 32 * HEX_WARPS_PER_BLOCK)
-int bn_b200_gt_inv_batch(const bn_gt* a, bn_gt* out, size_t n) { return bn_b200_gt_inv2_batch(a, a, out, n); }
-int bn_b200_gt_inv_batch_dev(const bn_gt* d_a, bn_gt* d_out, size_t n, void* stream) {
-    return bn_b200_gt_inv2_batch_dev(d_a, d_a, d_out, n, stream);
-}
-
-static int fq_chain_launch(const void* a, const void* b, void* o, size_t n, uint32_t iters, cudaStream_t st) {
-    if (n == 0) return 0;
-    k_fq_mul_chain<<<blocks_for(n, 256), 256, 0, st>>>(W(a), W(b), W(o), n, iters);
-    g_launches += 1;
-    CU(cudaGetLastError());
-    return 0;
-}
-int bn_b200_fq_mul_chain_dev(const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n, uint32_t iters, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (n && (!d_a || !d_b || !d_out)) return fail(BN_B200_EINVAL, "null pointer");
-    return fq_chain_launch(d_a, d_b, d_out, n, iters, stream ? (cudaStream_t)stream : g.stream);
-}
-int bn_b200_fq_mul_chain(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, uint32_t iters) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (n == 0) return 0;
-    if (!a || !b || !out) return fail(BN_B200_EINVAL, "null pointer");
-    return host_call(a, n * 32, b, n * 32, out, n * 32, [&](void* x, void* y, void* o, cudaStream_t st) {
-        return fq_chain_launch(x, y, o, n, iters, st);
-    });
-}
-
-/* calibration: run `blocks` x 256 threads of pure IMAD.WIDE.U32 (32 per loop trip, `iters` trips) on `stream`. */
-int bn_b200_imad_peak_dev(uint32_t* d_scratch, uint32_t blocks, uint32_t iters, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (!d_scratch) return fail(BN_B200_EINVAL, "null pointer");
-    k_imad_peak<<<blocks, 256, 0, stream ? (cudaStream_t)stream : g.stream>>>(d_scratch, iters, 1u);
-    g_launches += 1;
-    CU(cudaGetLastError());
-    return 0;
-}
-
-int bn_b200_fr_op_batch_dev(int op, const bn_fr* d_a, const bn_fr* d_b, bn_fr* d_out, size_t n, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (op < 0 || op > 4) return fail(BN_B200_EINVAL, "bad Fr op");
-    if (n && (!d_a || !d_out || (op <= 2 && !d_b))) return fail(BN_B200_EINVAL, "null pointer");
-    if (n == 0) return 0;
-    k_fr_op<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(W(d_a), W(d_b), W(d_out), n, op);
-    g_launches += 1;
-    CU(cudaGetLastError());
-    return 0;
-}
-int bn_b200_fr_op_batch(int op, const bn_fr* a, const bn_fr* b, bn_fr* out, size_t n) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    int rc = ensure_ready();
-    if (rc) return rc;
-    if (op < 0 || op > 4) return fail(BN_B200_EINVAL, "bad Fr op");
-    if (n == 0) return 0;
-    if (!a || !out || (op <= 2 && !b)) return fail(BN_B200_EINVAL, "null pointer");
-    return host_call(a, n * sizeof(bn_fr), b ? b : a, n * sizeof(bn_fr), out, n * sizeof(bn_fr),
-                     [&](void* x, void* y, void* o, cudaStream_t st) {
-                         k_fr_op<<<blocks_for(n, 128), 128, 0, st>>>(W(x), W(y), W(o), n, op);
-                         g_launches += 1;
-                         CU(cudaGetLastError());
-                         return 0;
-                     });
-}
-#define DEFINE_NORMALIZE(NAME, KERNEL, T)                                                                          \
-    int bn_b200_##NAME##_normalize_batch_dev(const T* d_p, T* d_out, size_t n, void* stream) {                      \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
-        int rc = ensure_ready();                                                                                    \
-        if (rc) return rc;                                                                                          \
-        if (n && (!d_p || !d_out)) return fail(BN_B200_EINVAL, "null pointer");                                     \
-        if (n == 0) return 0;                                                                                       \
-        KERNEL<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(W(d_p), W(d_out), n);      \
-        g_launches += 1;                                                                                            \
-        CU(cudaGetLastError());                                                                                     \
-        return 0;                                                                                                   \
-    }                                                                                                               \
-    int bn_b200_##NAME##_normalize_batch(const T* p, T* out, size_t n) {                                            \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
-        int rc = ensure_ready();                                                                                    \
-        if (rc) return rc;                                                                                          \
-        if (n == 0) return 0;                                                                                       \
-        if (!p || !out) return fail(BN_B200_EINVAL, "null pointer");                                                \
-        return host_call(p, n * sizeof(T), p, sizeof(T), out, n * sizeof(T),                                        \
-                         [&](void* x, void*, void* o, cudaStream_t st) {                                            \
-                             KERNEL<<<blocks_for(n, 128), 128, 0, st>>>(W(x), W(o), n);                             \
-                             g_launches += 1;                                                                       \
-                             CU(cudaGetLastError());                                                                \
-                             return 0;                                                                              \
-                         });                                                                                        \
-    }
-#define DEFINE_CHECK(NAME, KERNEL, T)                                                                              \
-    int bn_b200_##NAME##_check_batch_dev(const T* d_p, uint8_t* d_ok, size_t n, void* stream) {                     \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
-        int rc = ensure_ready();                                                                                    \
-        if (rc) return rc;                                                                                          \
-        if (n && (!d_p || !d_ok)) return fail(BN_B200_EINVAL, "null pointer");                                      \
-        if (n == 0) return 0;                                                                                       \
-        KERNEL<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(W(d_p), d_ok, n);          \
-        g_launches += 1;                                                                                            \
-        CU(cudaGetLastError());                                                                                     \
-        return 0;                                                                                                   \
-    }                                                                                                               \
-    int bn_b200_##NAME##_check_batch(const T* p, uint8_t* ok, size_t n) {                                           \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
-        int rc = ensure_ready();                                                                                    \
-        if (rc) return rc;                                                                                          \
-        if (n == 0) return 0;                                                                                       \
-        if (!p || !ok) return fail(BN_B200_EINVAL, "null pointer");                                                 \
-        return host_call(p, n * sizeof(T), p, sizeof(T), ok, n,                                                     \
-                         [&](void* x, void*, void* o, cudaStream_t st) {                                            \
-                             KERNEL<<<blocks_for(n, 128), 128, 0, st>>>(W(x), (uint8_t*)o, n);                      \
-                             g_launches += 1;                                                                       \
-                             CU(cudaGetLastError());                                                                \
-                             return 0;                                                                              \
-                         });                                                                                        \
-    }
-DEFINE_CHECK(g1, k_g1_check, bn_g1)
-DEFINE_CHECK(g2, k_g2_check, bn_g2)
-DEFINE_NORMALIZE(g1, k_g1_normalize, bn_g1)
-DEFINE_NORMALIZE(g2, k_g2_normalize, bn_g2)
-
-
-// ---- wire format entry points (row f-3) ---------------------------------------------------------------------------
-#define DEFINE_ENCODE(NAME, KERNEL, T, REC)                                                                         \
-    int bn_b200_##NAME##_encode_batch_dev(const T* d_p, uint8_t* d_out, size_t n, void* stream) {                     \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
-        int rc = ensure_ready();                                                                                    \
-        if (rc) return rc;                                                                                          \
-        if (n && (!d_p || !d_out)) return fail(BN_B200_EINVAL, "null pointer");                                     \
-        if (n == 0) return 0;                                                                                       \
-        KERNEL<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(W(d_p), d_out, n);         \
-        g_launches += 1;                                                                                            \
-        CU(cudaGetLastError());                                                                                     \
-        return 0;                                                                                                   \
-    }                                                                                                               \
-    int bn_b200_##NAME##_encode_batch(const T* p, uint8_t* out, size_t n) {                                          \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
-        int rc = ensure_ready();                                                                                    \
-        if (rc) return rc;                                                                                          \
-        if (n == 0) return 0;                                                                                       \
-        if (!p || !out) return fail(BN_B200_EINVAL, "null pointer");                                                \
-        return host_call(p, n * sizeof(T), p, sizeof(T), out, n * (size_t)(REC),                                    \
-                         [&](void* x, void*, void* o, cudaStream_t st) {                                            \
-                             KERNEL<<<blocks_for(n, 128), 128, 0, st>>>(W(x), (uint8_t*)o, n);                      \
-                             g_launches += 1;                                                                       \
-                             CU(cudaGetLastError());                                                                \
-                             return 0;                                                                              \
-                         });                                                                                        \
-    }
-#define DEFINE_DECODE(NAME, KERNEL, T, REC)                                                                         \
-    int bn_b200_##NAME##_decode_batch_dev(const uint8_t* d_in, T* d_out, uint8_t* d_status, size_t n, void* stream) { \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
-        int rc = ensure_ready();                                                                                    \
-        if (rc) return rc;                                                                                          \
-        if (n && (!d_in || !d_out || !d_status)) return fail(BN_B200_EINVAL, "null pointer");                       \
-        if (n == 0) return 0;                                                                                       \
-        KERNEL<<<blocks_for(n, 128), 128, 0, stream ? (cudaStream_t)stream : g.stream>>>(d_in, W(d_out), d_status, n); \
-        g_launches += 1;                                                                                            \
-        CU(cudaGetLastError());                                                                                     \
-        return 0;                                                                                                   \
-    }                                                                                                               \
-    int bn_b200_##NAME##_decode_batch(const uint8_t* in, T* out, uint8_t* status, size_t n) {                        \
-        std::lock_guard<std::mutex> lk(g_mu);                                                                       \
-        int rc = ensure_ready();                                                                                    \
-        if (rc) return rc;                                                                                          \
-        if (n == 0) return 0;                                                                                       \
-        if (!in || !out || !status) return fail(BN_B200_EINVAL, "null pointer");                                    \
-        /* staging: records | points followed by the status bytes */                                               \
-        const size_t pts = n * sizeof(T);                                                                           \
-        if ((rc = ensure_buf(&g.stage[0], &g.stage_cap[0], n * (size_t)(REC)))) return rc;                          \
-        if ((rc = ensure_buf(&g.stage[2], &g.stage_cap[2], pts + n))) return rc;                                    \
-        CU(cudaMemcpyAsync(g.stage[0], in, n * (size_t)(REC), cudaMemcpyHostToDevice, g.stream));                   \
-        uint8_t* d_status = (uint8_t*)g.stage[2] + pts;                                                             \
-        KERNEL<<<blocks_for(n, 128), 128, 0, g.stream>>>((const uint8_t*)g.stage[0], W(g.stage[2]), d_status, n);   \
-        g_launches += 1;                                                                                            \
-        CU(cudaGetLastError());                                                                                     \
-        CU(cudaMemcpyAsync(out, g.stage[2], pts, cudaMemcpyDeviceToHost, g.stream));                                \
-        CU(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, g.stream));                                 \
-        CU(cudaStreamSynchronize(g.stream));                                                                        \
-        return 0;                                                                                                   \
-    }
-DEFINE_ENCODE(g1, k_g1_encode, bn_g1, 65)
-DEFINE_ENCODE(g2, k_g2_encode, bn_g2, 129)
-DEFINE_ENCODE(fr, k_fr_encode, bn_fr, 32)
-DEFINE_DECODE(g1, k_g1_decode, bn_g1, 65)
-DEFINE_DECODE(g2, k_g2_decode, bn_g2, 129)
-DEFINE_DECODE(fr, k_fr_decode, bn_fr, 32)
-
-}  // extern "C"
+#include "capi.inc"

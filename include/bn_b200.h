@@ -15,11 +15,15 @@
  *     bn_b200_last_error() gives a message for the last failure on the calling thread.
  *   - caller owns every buffer; the library owns its stream, scratch memory and events.
  *   - host-pointer entry points copy H2D, run the kernels and copy D2H before returning (bn_b200_pairing_batch writes
- *     a page-locked, device-mapped `out` buffer directly from the last kernel instead of a D2H pass).
- *   - *_dev entry points take DEVICE pointers (same layouts) and enqueue on `stream`
- *     (a cudaStream_t cast to void*; NULL = the library's own stream) without synchronising.
- *   - thread-safe: calls are serialised by an internal lock (the crate's types are Send + Sync,
- *     reference src/lib.rs:56-66).
+ *     a page-locked, device-mapped `out` buffer directly from the last kernel instead of a D2H pass).  With several
+ *     GPUs bound (bn_b200_init_multi) a host-pointer batch is split into contiguous ranges, one per GPU, inside the call.
+ *   - *_dev entry points take DEVICE pointers (same layouts) and enqueue on `stream` without synchronising.  `stream` is a
+ *     cudaStream_t cast to void*.  NULL is NOT the caller's default stream: it selects the library's own non-blocking
+ *     stream of that device (pass cudaStreamLegacy / cudaStreamPerThread explicitly to use a default stream).  The call runs
+ *     on the bound device that owns the pointers.  Calls on different streams are safe: the library orders its own scratch
+ *     memory between them with events; the caller orders its own buffers.
+ *   - thread-safe (the crate's types are Send + Sync, reference src/lib.rs:56-66): one lock per device, held while work is
+ *     enqueued, released before the host waits; the CUDA device of the calling thread is saved and restored by every call.
  *   - there is NO CPU fallback: without a CUDA device every call fails with BN_B200_ENODEV.
  */
 #ifndef BN_B200_H
@@ -43,14 +47,42 @@ typedef struct { uint64_t c[2][3][2][4]; } bn_gt;                 /* bn::Gt  src
 #define BN_B200_EINVAL (-3)   /* null pointer or bad argument */
 #define BN_B200_ENOMEM (-4)   /* device allocation failed */
 
-/* Select the CUDA device for this process (one process per GPU), create the stream. Idempotent. */
+/* Bind ONE CUDA device to this process (one process per GPU) and create its streams.  Idempotent; binding a different
+ * device tears the previous binding down first (streams, scratch and staging memory are released). */
 int bn_b200_init(int device);
+/* Bind devices 0 .. n_gpus-1 (n_gpus <= 0: every visible device, at most 8) to THIS process: the library then owns one
+ * context (streams, scratch, staging) per GPU and host-pointer batches are sharded over all of them from one call
+ * ("bn_b200_init(int n_gpus) creates streams").  No torch / NCCL involved: shards are
+ * independent, results land in the caller's buffer (zero-copy stores into page-locked memory, or one D2H per device). */
+int bn_b200_init_multi(int n_gpus);
+/* Number of devices currently bound (0 before init). */
+int bn_b200_device_count(void);
 int bn_b200_shutdown(void);
+/* A device is only given a shard of at least `elements` (default 2048; 0 restores it): small batches stay on one GPU. */
+int bn_b200_set_min_shard(size_t elements);
+/* Page-locked host memory mapped into every bound device, for callers that do not link the CUDA runtime themselves:
+ * inputs in it are copied without staging, and an `out` buffer in it is written directly by the last pairing kernel. */
+int bn_b200_alloc_pinned(void** p, size_t bytes);
+int bn_b200_free_pinned(void* p);
+/* OR of the bound devices' error words (bit 0: a line-ring / TMA wait timed out inside a pairing kernel: results of that
+ * call are invalid).  Host-pointer calls check it themselves and return BN_B200_ECUDA; *_dev callers poll it here.
+ * Synchronises the devices.  clear != 0 resets the words.  Negative: BN_B200_E*. */
+int bn_b200_device_error(int clear);
 const char* bn_b200_last_error(void);
 /* Number of SMs of the active device (0 before init). */
 int bn_b200_sm_count(void);
 /* Line evaluations per pairing in the library's Miller schedule (88: NAF walk of 6u+2; the reference's binary walk has 102). */
 int bn_b200_num_lines(void);
+
+/* Constants of the crate's API as byte images (pure data; no device needed).
+ * replaces Fr::one src/lib.rs:21, Group::one / zero src/lib.rs:84-85, 127-128 (src/groups/mod.rs:208-218, 356-390), Gt::one src/lib.rs:170.
+ * (Fr::zero is all-zero bytes.) */
+int bn_b200_fr_one(bn_fr* out);
+int bn_b200_g1_one(bn_g1* out);
+int bn_b200_g2_one(bn_g2* out);
+int bn_b200_g1_zero(bn_g1* out);
+int bn_b200_g2_zero(bn_g2* out);
+int bn_b200_gt_one(bn_gt* out);
 
 /* pairing(p, q) for n independent pairs.              replaces bn::pairing, src/lib.rs:181-183
  * (groups::pairing src/groups/mod.rs:764-771: to_affine + precompute + miller_loop + final_exponentiation;
@@ -78,6 +110,37 @@ int bn_b200_g1_mul_batch_dev(const bn_g1* d_p, const bn_fr* d_k, bn_g1* d_out, s
 int bn_b200_g2_mul_batch(const bn_g2* p, const bn_fr* k, bn_g2* out, size_t n);
 int bn_b200_g2_mul_batch_dev(const bn_g2* d_p, const bn_fr* d_k, bn_g2* d_out, size_t n, void* stream);
 
+/* Group law at the boundary.       replaces `impl Add / Sub / Neg for G1, G2`, src/lib.rs:97-114, 140-157
+ * (-> src/groups/mod.rs:272-347: add returns the other operand when one is zero, doubles when the operands are equal, and
+ * P + (-P) falls through the general formula to a z = 0 triple; neg leaves zero unchanged; sub = a + (-b)) and G::double
+ * (src/groups/mod.rs:228-247).  Outputs are the crate's un-normalised Jacobian triples, limb for limb.
+ * bn_b200_g{1,2}_op_batch: op 0 a + b, 1 a - b, 2 -a, 3 a.double() (b may be NULL for op >= 2). */
+int bn_b200_g1_op_batch(int op, const bn_g1* a, const bn_g1* b, bn_g1* out, size_t n);
+int bn_b200_g1_op_batch_dev(int op, const bn_g1* d_a, const bn_g1* d_b, bn_g1* d_out, size_t n, void* stream);
+int bn_b200_g2_op_batch(int op, const bn_g2* a, const bn_g2* b, bn_g2* out, size_t n);
+int bn_b200_g2_op_batch_dev(int op, const bn_g2* d_a, const bn_g2* d_b, bn_g2* d_out, size_t n, void* stream);
+int bn_b200_g1_add_batch(const bn_g1* a, const bn_g1* b, bn_g1* out, size_t n);
+int bn_b200_g1_add_batch_dev(const bn_g1* d_a, const bn_g1* d_b, bn_g1* d_out, size_t n, void* stream);
+int bn_b200_g1_sub_batch(const bn_g1* a, const bn_g1* b, bn_g1* out, size_t n);
+int bn_b200_g1_sub_batch_dev(const bn_g1* d_a, const bn_g1* d_b, bn_g1* d_out, size_t n, void* stream);
+int bn_b200_g1_neg_batch(const bn_g1* a, bn_g1* out, size_t n);
+int bn_b200_g1_neg_batch_dev(const bn_g1* d_a, bn_g1* d_out, size_t n, void* stream);
+int bn_b200_g1_double_batch(const bn_g1* a, bn_g1* out, size_t n);
+int bn_b200_g1_double_batch_dev(const bn_g1* d_a, bn_g1* d_out, size_t n, void* stream);
+int bn_b200_g2_add_batch(const bn_g2* a, const bn_g2* b, bn_g2* out, size_t n);
+int bn_b200_g2_add_batch_dev(const bn_g2* d_a, const bn_g2* d_b, bn_g2* d_out, size_t n, void* stream);
+int bn_b200_g2_sub_batch(const bn_g2* a, const bn_g2* b, bn_g2* out, size_t n);
+int bn_b200_g2_sub_batch_dev(const bn_g2* d_a, const bn_g2* d_b, bn_g2* d_out, size_t n, void* stream);
+int bn_b200_g2_neg_batch(const bn_g2* a, bn_g2* out, size_t n);
+int bn_b200_g2_neg_batch_dev(const bn_g2* d_a, bn_g2* d_out, size_t n, void* stream);
+int bn_b200_g2_double_batch(const bn_g2* a, bn_g2* out, size_t n);
+int bn_b200_g2_double_batch_dev(const bn_g2* d_a, bn_g2* d_out, size_t n, void* stream);
+/* eq[i] = (a[i] == b[i]) as group elements.            replaces `PartialEq for G` (projective), src/groups/mod.rs:83-109 */
+int bn_b200_g1_eq_batch(const bn_g1* a, const bn_g1* b, uint8_t* eq, size_t n);
+int bn_b200_g1_eq_batch_dev(const bn_g1* d_a, const bn_g1* d_b, uint8_t* d_eq, size_t n, void* stream);
+int bn_b200_g2_eq_batch(const bn_g2* a, const bn_g2* b, uint8_t* eq, size_t n);
+int bn_b200_g2_eq_batch_dev(const bn_g2* d_a, const bn_g2* d_b, uint8_t* d_eq, size_t n, void* stream);
+
 /* out[i] = a[i].pow(k[i]).                            replaces Gt::pow, src/lib.rs:171 (FieldElement::pow, src/fields/mod.rs:35-46) */
 int bn_b200_gt_pow_batch(const bn_gt* a, const bn_fr* k, bn_gt* out, size_t n);
 int bn_b200_gt_pow_batch_dev(const bn_gt* d_a, const bn_fr* d_k, bn_gt* d_out, size_t n, void* stream);
@@ -88,6 +151,18 @@ int bn_b200_gt_mul_batch_dev(const bn_gt* d_a, const bn_gt* d_b, bn_gt* d_out, s
 /* out[i] = a[i].inverse() (a[i] != 0).                 replaces Gt::inverse, src/lib.rs:172 */
 int bn_b200_gt_inv_batch(const bn_gt* a, bn_gt* out, size_t n);
 int bn_b200_gt_inv_batch_dev(const bn_gt* d_a, bn_gt* d_out, size_t n, void* stream);
+
+/* out[i] = a[i].exp_by_neg_z() evaluated as the reference does (binary cyclotomic_pow(u), literal Granger-Scott squaring,
+ * conjugate): defined for ANY Fq12 input.      replaces Fq12::exp_by_neg_z, src/fields/fq12.rs:97-101, 178-246
+ * (the building block of final_exponentiation; exposed so the reference's test_cyclotomic_exp vector, src/fields/mod.rs:171-201,
+ * runs on the device). */
+int bn_b200_gt_exp_by_neg_z_batch(const bn_gt* a, bn_gt* out, size_t n);
+int bn_b200_gt_exp_by_neg_z_batch_dev(const bn_gt* d_a, bn_gt* d_out, size_t n, void* stream);
+
+/* out[i] = a[i].pow(e[i]).                             replaces Fr::pow, src/lib.rs:24 (FieldElement::pow, src/fields/mod.rs:35-46;
+ * the exponent is U256::from(e[i])). */
+int bn_b200_fr_pow_batch(const bn_fr* a, const bn_fr* e, bn_fr* out, size_t n);
+int bn_b200_fr_pow_batch_dev(const bn_fr* d_a, const bn_fr* d_e, bn_fr* d_out, size_t n, void* stream);
 
 /* Batched Fr arithmetic.            replaces bn::Fr Mul/Add/Sub/Neg/inverse, src/lib.rs:25, 32-54
  * op: 0 a*b, 1 a+b, 2 a-b, 3 -a, 4 a.inverse() (inverse of zero yields zero; the crate returns None).  b may be NULL for op >= 3. */
@@ -141,6 +216,10 @@ int bn_b200_fr_decode_batch_dev(const uint8_t* d_in, bn_fr* d_out, uint8_t* d_st
 int bn_b200_fq_mul_chain(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, uint32_t iters);
 int bn_b200_fq_mul_chain_dev(const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n, uint32_t iters, void* stream);
 
+/* x <- x^2 (Montgomery, mod q) repeated `iters` times: the dedicated squaring (108 IMAD.WIDE against 136). */
+int bn_b200_fq_sqr_chain(const uint64_t* a, uint64_t* out, size_t n, uint32_t iters);
+int bn_b200_fq_sqr_chain_dev(const uint64_t* d_a, uint64_t* d_out, size_t n, uint32_t iters, void* stream);
+
 /* Calibration kernel for the roofline denominator: `blocks` x 256 threads each issue iters*32 independent
  * IMAD.WIDE.U32 (the instruction every Fq product is made of).  d_scratch: >= 4 bytes of device memory. */
 int bn_b200_imad_peak_dev(uint32_t* d_scratch, uint32_t blocks, uint32_t iters, void* stream);
@@ -156,6 +235,10 @@ int bn_b200_set_profiling(int enable);
 int bn_b200_last_pairing_kernel_ms(float ms[2]);
 /* Same, three values: ms[0] = line schedule, ms[1] = Miller loop (k_miller), ms[2] = final exponentiation (k_fexp). */
 int bn_b200_last_pairing_kernel_ms3(float ms[3]);
+/* Name of the i-th kernel of the pairing path (i = 0, 1, 2: the three values of bn_b200_last_pairing_kernel_ms3), NULL beyond. */
+const char* bn_b200_pairing_kernel_name(int i);
+/* Library-owned device scratch per pairing in flight (line coefficients + flag), bytes. */
+size_t bn_b200_scratch_bytes_per_pairing(void);
 /* Number of kernels this library has launched since init (for the bench's gpu_launches claim). */
 unsigned long long bn_b200_launch_count(void);
 

@@ -250,47 +250,7 @@ def test_fused_pairing_pow(bn):
     assert np.array_equal(ss[0], ss[1]) and np.array_equal(ss[1], ss[2])
 
 
-def test_full_size_config4_properties(bn):
-    """BASELINE config 4 size (2^14): the oracle cannot finish this in seconds, so check size-independent
-    properties: a sampled subset is bit-exact vs the oracle, and e(P, Q)*e(-P, Q) == 1 for every pair."""
-    n = 1 << 14
-    gen1, gen2 = cref.g1_generator(), cref.g2_generator()
-    a = util.synth_scalars(0xB2000004, n)
-    b = util.synth_scalars(0xB2000014, n)
-    g1 = bn.g1_mul_batch(np.repeat(gen1, n, axis=0), a)   # on-device input generation (row f-2)
-    g2 = bn.g2_mul_batch(np.repeat(gen2, n, axis=0), b)
-    gt = bn.pairing_batch(g1, g2)
-    idx = np.arange(0, n, n // 64)
-    assert np.array_equal(gt[idx], cref.pairing_batch(g1[idx], g2[idx], 8))
-    neg = g1.copy()
-    q = np.frombuffer(o.Q.to_bytes(32, "little"), dtype="<u8")
-    # -P: y -> q - y on the Montgomery limbs (y != 0 for points of odd order)
-    y = [int.from_bytes(r.tobytes(), "little") for r in g1[:, 4:8]]
-    neg[:, 4:8] = np.stack([util.words((o.Q - v).to_bytes(32, "little")) for v in y])
-    prod = bn.gt_mul_batch(gt, bn.pairing_batch(neg, g2))
-    one = util.gt_img(o.FQ12_ONE)
-    assert (prod == one[None]).all()
-
-
-def test_config5_size_single_gpu(bn):
-    """BASELINE config 5's 2^17 pairs on ONE GPU (the per-rank shard code path with an 8x larger batch):
-    sampled oracle parity + e(P,Q)*e(-P,Q) == 1 over the whole batch."""
-    n = 1 << 17
-    gen1, gen2 = cref.g1_generator(), cref.g2_generator()
-    a = np.tile(util.synth_scalars(0xB2000005, 1 << 11), (n >> 11, 1))
-    b = np.tile(util.synth_scalars(0xB2000015, 1 << 11), (n >> 11, 1))
-    b[:, 0] ^= np.arange(n, dtype=np.uint64) & np.uint64(0xFF)  # perturb the low limb: still canonical (< r)
-    g1 = bn.g1_mul_batch(np.repeat(gen1, n, axis=0), a)
-    g2 = bn.g2_mul_batch(np.repeat(gen2, n, axis=0), b)
-    gt = bn.pairing_batch(g1, g2)
-    idx = np.concatenate([np.arange(0, n, n // 32), [n - 1, n - 2, n - 5, n - 6]])
-    assert np.array_equal(gt[idx], cref.pairing_batch(g1[idx], g2[idx], 8))
-    neg = g1.copy()
-    y = [int.from_bytes(r.tobytes(), "little") for r in g1[: 1 << 11, 4:8]]
-    negy = np.stack([util.words((o.Q - v).to_bytes(32, "little")) for v in y])
-    neg[:, 4:8] = np.tile(negy, (n >> 11, 1))   # a is tiled, so P (hence -P) repeats every 2^11 entries
-    prod = bn.gt_mul_batch(gt, bn.pairing_batch(neg, g2))
-    assert (prod == util.gt_img(o.FQ12_ONE)[None]).all()
+# (parity at the BASELINE config sizes: tests/test_gpu_sizes.py)
 
 
 def test_device_pointer_api_with_torch(bn):
