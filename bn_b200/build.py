@@ -47,5 +47,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """A/B build: bn_b200/libv_<name>.so with extra -D flags (select it at run time with BN_B200_SO=<path>)."""
+    out = os.path.join(HERE, "libv_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(CSRC, "kernels.cu")]
+    subprocess.check_call(cmd, cwd=HERE)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -21,7 +21,7 @@ struct FqOps {
     static BN_HD T sub(const T& a, const T& b) { return fp_sub<MQ>(a, b); }
     static BN_HD T neg(const T& a) { return fp_neg<MQ>(a); }
     static BN_HD T mul(const T& a, const T& b) { return fp_mul_ni<MQ>(a, b); }
-    static BN_HD T sqr(const T& a) { return fp_mul_ni<MQ>(a, a); }
+    static BN_HD T sqr(const T& a) { return fp_sqr_ni<MQ>(a); }
     static BN_HD bool is_zero(const T& a) { return fp_is_zero(a); }
     static BN_HD bool eq(const T& a, const T& b) { return fp_eq(a, b); }
     static BN_HD T zero() { return fp_zero(); }

@@ -88,6 +88,72 @@ BN_HD void mad_row4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32
 #endif
 }
 
+// Shorter chains for the squaring triangle: acc[0 .. 2N) += {x0 .. x(N-1)} * y, carry-out added into acc[2N].
+BN_HD void mad_row3(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y) {
+#if defined(__CUDA_ARCH__)
+    BN_MAD_ASM("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(y));
+#else
+    const uint32_t x[3] = {x0, x1, x2};
+    uint64_t c = 0;
+    for (int j = 0; j < 3; j++) {
+        uint64_t p = (uint64_t)x[j] * y;
+        uint64_t t = (uint64_t)acc[2 * j] + (uint32_t)p + c;
+        acc[2 * j] = (uint32_t)t;
+        t = (uint64_t)acc[2 * j + 1] + (p >> 32) + (t >> 32);
+        acc[2 * j + 1] = (uint32_t)t;
+        c = t >> 32;
+    }
+    acc[6] += (uint32_t)c;
+#endif
+}
+BN_HD void mad_row2(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t y) {
+#if defined(__CUDA_ARCH__)
+    BN_MAD_ASM("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+        : "r"(x0), "r"(x1), "r"(y));
+#else
+    const uint32_t x[2] = {x0, x1};
+    uint64_t c = 0;
+    for (int j = 0; j < 2; j++) {
+        uint64_t p = (uint64_t)x[j] * y;
+        uint64_t t = (uint64_t)acc[2 * j] + (uint32_t)p + c;
+        acc[2 * j] = (uint32_t)t;
+        t = (uint64_t)acc[2 * j + 1] + (p >> 32) + (t >> 32);
+        acc[2 * j + 1] = (uint32_t)t;
+        c = t >> 32;
+    }
+    acc[4] += (uint32_t)c;
+#endif
+}
+BN_HD void mad_row1(uint32_t* acc, uint32_t x0, uint32_t y) {
+#if defined(__CUDA_ARCH__)
+    BN_MAD_ASM("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
+        : "r"(x0), "r"(y));
+#else
+    uint64_t p = (uint64_t)x0 * y;
+    uint64_t t = (uint64_t)acc[0] + (uint32_t)p;
+    acc[0] = (uint32_t)t;
+    t = (uint64_t)acc[1] + (p >> 32) + (t >> 32);
+    acc[1] = (uint32_t)t;
+    acc[2] += (uint32_t)(t >> 32);
+#endif
+}
+
 // Same, without a carry-out limb (caller proved the carry is zero).
 BN_HD void mad_row4_nc(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
 #if defined(__CUDA_ARCH__)
@@ -583,6 +649,47 @@ BN_HD void wide_mul(Wide& T, const Fp& a, const Fp& b) {
     for (int i = 0; i < 16; i++) T.w[i] = E[i];
     add16_shift1(T.w, O);
 }
+// T = a^2 as a 512-bit integer: the 28 cross products a_i a_j (i < j) in the (E, O) layout of eo_row, doubled, plus the
+// eight squares a_i^2, which tile the 512 bits exactly (a_i^2 occupies limbs 2i, 2i + 1): 36 IMAD.WIDE against 64.
+BN_HD void wide_sqr(Wide& T, const Fp& a) {
+    uint32_t E[18], O[16];
+    BN_UNROLL
+    for (int i = 0; i < 18; i++) E[i] = 0;
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) O[i] = 0;
+    const uint32_t* v = a.v;
+    // row i multiplies by y = a_i and takes the limbs j > i; a product a_j y lands at limb position i + j: even
+    // positions live in E (index = position), odd ones in O (index = position - 1)
+    mad_row3(&E[2], v[2], v[4], v[6], v[0]);          // i = 0: j = 2, 4, 6   -> positions 2, 4, 6
+    mad_row4(&O[0], v[1], v[3], v[5], v[7], v[0]);    //        j = 1, 3, 5, 7 -> positions 1, 3, 5, 7
+    mad_row3(&O[2], v[2], v[4], v[6], v[1]);          // i = 1: j = 2, 4, 6   -> positions 3, 5, 7
+    mad_row3(&E[4], v[3], v[5], v[7], v[1]);          //        j = 3, 5, 7   -> positions 4, 6, 8
+    mad_row2(&E[6], v[4], v[6], v[2]);                // i = 2: j = 4, 6      -> positions 6, 8
+    mad_row3(&O[4], v[3], v[5], v[7], v[2]);          //        j = 3, 5, 7   -> positions 5, 7, 9
+    mad_row2(&O[6], v[4], v[6], v[3]);                // i = 3: j = 4, 6      -> positions 7, 9
+    mad_row2(&E[8], v[5], v[7], v[3]);                //        j = 5, 7      -> positions 8, 10
+    mad_row1(&E[10], v[6], v[4]);                     // i = 4: j = 6         -> position 10
+    mad_row2(&O[8], v[5], v[7], v[4]);                //        j = 5, 7      -> positions 9, 11
+    mad_row1(&O[10], v[6], v[5]);                     // i = 5: j = 6         -> position 11
+    mad_row1(&E[12], v[7], v[5]);                     //        j = 7         -> position 12
+    mad_row1(&O[12], v[7], v[6]);                     // i = 6: j = 7         -> position 13
+    // cross = E + 2^32 O (< 2^511), doubled
+    uint32_t c[16];
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) c[i] = E[i];
+    add16_shift1(c, O);
+    BN_UNROLL
+    for (int i = 15; i > 0; i--) c[i] = (c[i] << 1) | (c[i - 1] >> 31);
+    c[0] <<= 1;
+    // diagonal: eight independent 64-bit squares
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) {
+        const uint64_t d = (uint64_t)v[i] * v[i];
+        T.w[2 * i] = (uint32_t)d;
+        T.w[2 * i + 1] = (uint32_t)(d >> 32);
+    }
+    add16(T.w, c);
+}
 // acc <<= 1 (value doubles; caller keeps it < 2^512)
 BN_HD void wide_dbl(Wide& acc) {
     BN_UNROLL
@@ -734,9 +841,17 @@ template <class M>
 BN_HD_NOINLINE Fp fp_mul_ni(Fp a, Fp b) {
     return fp_mul<M>(a, b);
 }
+// a^2 R^-1 mod p, canonical: dedicated squaring (36 + 72 IMAD against 64 + 72).   reference FieldElement::squared,
+// src/fields/mod.rs:31-33 (a * a there)
 template <class M>
 BN_HD Fp fp_sqr(const Fp& a) {
-    return fp_mul<M>(a, a);
+    Wide T;
+    wide_sqr(T, a);
+    return mont_reduce<M, 2>(T);
+}
+template <class M>
+BN_HD_NOINLINE Fp fp_sqr_ni(Fp a) {
+    return fp_sqr<M>(a);
 }
 // Montgomery -> plain integer (multiply by 1).   reference src/fields/fp.rs:15-22
 template <class M>
@@ -754,7 +869,7 @@ BN_HD_NOINLINE Fp fp_inv(Fp x) {
     // exponent p-2, MSB first; p-2 has bit 253 set.
     Fp r = x;
     for (int bit = 252; bit >= 0; bit--) {
-        r = fp_mul<M>(r, r);
+        r = fp_sqr<M>(r);
         uint32_t e = (bit < 32) ? (M::m(0) - 2u) : M::m(bit >> 5);  // p-2 only changes limb 0 (p odd, p0 >= 2)
         if ((e >> (bit & 31)) & 1u) r = fp_mul<M>(r, x);
     }

@@ -29,8 +29,31 @@
 // inversion, tests/host_emu binds them to a barrier exchange between six host threads and a Fermat inversion.
 #pragma once
 #include "fp2.cuh"
+#ifndef BN_F52
+#define BN_F52 1   // 1: Fq2 multiply-accumulate + reduction on the FP64 pipe (f52.cuh); 0: IMAD.WIDE accumulators (A/B)
+#endif
+#include "f52.cuh"
 
 namespace bn {
+
+#if BN_F52
+// Operand exchange in the FP64 form: a lane publishes an Fq2 value as three 5 x 52-bit factors (c0, c1, c0 + c1; D5x3,
+// one 144-byte slot) with c.put52, and the receivers name a published operand by a Ctx::Ref (c.ref(lane, slot) /
+// c.ref_or_zero(cond, lane, slot)) and load one factor at a time (c.ld5(ref, which)), so that only 2 x 5 doubles are live
+// next to the column accumulators.
+template <class Ctx>
+BN_HD void mac52_rr(const Ctx& c, Acc52& A, typename Ctx::Ref x, typename Ctx::Ref y) {
+    f52_mac(A.s0, c.ld5(x, 0), c.ld5(y, 0));
+    f52_mac(A.s1, c.ld5(x, 1), c.ld5(y, 1));
+    f52_mac(A.s2, c.ld5(x, 2), c.ld5(y, 2));
+}
+template <class Ctx>
+BN_HD void mac52_rv(const Ctx& c, Acc52& A, typename Ctx::Ref x, const D5x3& y) {
+    f52_mac(A.s0, c.ld5(x, 0), y.c0);
+    f52_mac(A.s1, c.ld5(x, 1), y.c1);
+    f52_mac(A.s2, c.ld5(x, 2), y.cs);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Lazy Fq2 multiply-accumulate on two merged 512-bit accumulators (arithmetic mod 2^512).
@@ -198,6 +221,24 @@ BN_HD Fp2 hx_conj(const Ctx& c, const Fp2& a) {
 template <class Ctx>
 BN_HD_NOINLINE Fp2 hx_mul(const Ctx c, Fp2 a, Fp2 b) {
     const int k = c.k();
+#if BN_F52
+    {
+        const Fp2 xa = c.mul_xi(a);
+        c.sync();
+        c.put52(0, a);
+        c.put52(1, xa);
+        c.put52(2, b);
+        c.sync();
+    }
+    Acc52 acc;
+    acc52_init(acc);
+#if defined(__CUDA_ARCH__)
+BN_UNROLL_N(BN_MUL_UNROLL)
+#endif
+    for (int s = 0; s < 6; s++)  // receiver k takes a_j from j = k - s (mod 6); (j, s) wraps past w^5 iff s > k
+        mac52_rr(c, acc, c.ref(mod6(k + 6 - s), s > k ? 1 : 0), c.ref(s, 2));
+    return acc52_reduce<6>(acc);
+#else
     c.sync();
     c.put(0, a);
     c.put(1, c.mul_xi(a));
@@ -215,6 +256,7 @@ BN_UNROLL_N(BN_MUL_UNROLL)
         mac_fp2(acc, x, y);
     }
     return reduce2(acc);
+#endif
 }
 
 // square.  reference src/fields/fq12.rs:275-282.  21 distinct products in 4 lock-step rounds:
@@ -227,13 +269,24 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
     {
         Fp2 xa = c.mul_xi(a);
         c.sync();
+#if BN_F52
+        c.put52(0, a);
+        c.put52(1, xa);
+        c.put52(2, fp2_dbl(fp2_select(k >= 4, xa, a)));
+#else
         c.put(0, a);
         c.put(1, xa);
         c.put(2, fp2_dbl(fp2_select(k >= 4, xa, a)));  // doubled operand: 2 a_k on lanes 0..3, 2 xi a_k on lanes 4,5
+#endif
         c.sync();
     }
+#if BN_F52
+    Acc52 acc;
+    acc52_init(acc);
+#else
     typename AccSel<BN_ACC_SQR>::type acc;
     acck_init(acc);
+#endif
 #if defined(__CUDA_ARCH__)
 BN_UNROLL_N(BN_SQR_UNROLL)
 #endif
@@ -248,11 +301,19 @@ BN_UNROLL_N(BN_SQR_UNROLL)
         const int xsrc = nib(xs, k);
         // slot: doubled (2) in rounds 0-1 and for sources 3,4 in round 2; plain (0) otherwise in round 2; xi (1) in round 3
         const int xslot = r < 2 ? 2 : (r == 2 ? ((xsrc == 3 || xsrc == 4) ? 2 : 0) : 1);
+#if BN_F52
+        mac52_rr(c, acc, c.ref(xsrc, xslot), c.ref_or_zero(!(r == 3 && (k & 1) != 0), nib(ys, k), 0));
+#else
         Fp2 x = c.get(xsrc, xslot);
         Fp2 y = c.get_or_zero(!(r == 3 && (k & 1) != 0), nib(ys, k), 0);  // odd lanes idle in round 3: zero by address
         mac_fp2(acc, x, y);
+#endif
     }
+#if BN_F52
+    return acc52_reduce<4>(acc);
+#else
     return reduce2(acc);
+#endif
 }
 
 // product with the sparse line l0 + l3 w^3 + l4 w^4 (reference mul_by_024, src/fields/fq12.rs:107-176).
@@ -263,6 +324,18 @@ template <class Ctx, class LineSrc>
 BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, const LineSrc src, typename LineSrc::Handle h) {
     const int k = c.k();
     c.sync();
+#if BN_F52
+    c.put52(0, a);
+    c.sync();
+    Acc52 acc;
+    acc52_init(acc);
+#if defined(__CUDA_ARCH__)
+BN_UNROLL_N(BN_LINE_UNROLL)
+#endif
+    for (int r = 0; r < 3; r++)  // a_k, a_{k-3}, a_{k-4}; the line coefficient is converted by the receiver
+        mac52_rv(c, acc, c.ref(mod6(k + (r == 0 ? 0 : r == 1 ? 3 : 2)), 0), f52_from_fp2(src.coef(h, r)));
+    return acc52_reduce<3>(acc);
+#else
     c.put(0, a);
     c.sync();
     typename AccSel<BN_ACC_LINE>::type acc;
@@ -276,6 +349,7 @@ BN_UNROLL_N(BN_LINE_UNROLL)
         mac_fp2(acc, x, y);
     }
     return reduce2(acc);
+#endif
 }
 
 // product with an Fq6 element m0 + m1 v + m2 v^2 = m0 + m1 w^2 + m2 w^4 known to every lane.
@@ -285,6 +359,18 @@ BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx c, Fp2 a, Fp2 m0, Fp2 m1, Fp2 m2) {
     Fp2 m1k = fp2_select(k < 2, c.mul_xi(m1), m1);
     Fp2 m2k = fp2_select(k < 4, c.mul_xi(m2), m2);
     c.sync();
+#if BN_F52
+    c.put52(0, a);
+    c.sync();
+    Acc52 acc;
+    acc52_init(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = 0; r < 3; r++)  // a_k, a_{k-2}, a_{k-4}
+        mac52_rv(c, acc, c.ref(mod6(k + (r == 0 ? 0 : r == 1 ? 4 : 2)), 0), f52_from_fp2(fp2_select(r == 0, m0, fp2_select(r == 1, m1k, m2k))));
+    return acc52_reduce<3>(acc);
+#else
     c.put(0, a);
     c.sync();
     typename AccSel<BN_ACC_LINE>::type acc;
@@ -298,6 +384,7 @@ BN_HD_NOINLINE Fp2 hx_mul_fq6(const Ctx c, Fp2 a, Fp2 m0, Fp2 m1, Fp2 m2) {
         mac_fp2(acc, x, y);
     }
     return reduce2(acc);
+#endif
 }
 
 // Frobenius x -> x^(q^p), p in {1,2,3}: conj^p on each coefficient, times xi^(k (q^p-1)/6).
@@ -346,10 +433,17 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
         f1.c0 = fp_add_raw(f1.c0, v.c0);
         f1.c1 = fp_add_raw(f1.c1, v.c1);
     }
+#if BN_F52
+    Acc52 acc;
+    acc52_init(acc);
+    acc52_mac(acc, f52_from_fp2(f0), f52_from_fp2(f1));  // components < 2q, their sums < 4q < 2^256
+    Fp2 r = acc52_reduce<1>(acc);
+#else
     typename AccSel<BN_ACC_CYC>::type acc;
     acck_init(acc);
     mac_fp2(acc, f0, f1);
     Fp2 r = reduce2(acc);
+#endif
     // partner product: lane0 <- lane3, lane2 <- lane5, lane4 <- lane1
     c.put(2, r);
     c.sync();
@@ -416,12 +510,19 @@ BN_HD Fp2 hx_exp_by_neg_z_literal(const Ctx& c, const Fp2& a) {
 }
 
 // 1/f for f != 0.  reference src/fields/fq12.rs:284-292 -> fq6.rs:129-141 -> fq2.rs:125-136.
-// f^-1 = conj(f) * N^-1 with N = f * conj(f) in Fq6; the small Fq6/Fq2/Fq inversion chain is done
-// redundantly by every lane (it is a handful of Fq2 products next to one Fq inversion).
+// f^-1 = conj(f) * N^-1 with N = f * conj(f) in Fq6; the small Fq6/Fq2 chain down to ONE Fq inversion is done
+// redundantly by every lane (a handful of Fq2 products).  Split in two so that the Fq inversion itself can happen
+// anywhere in between -- in place (hx_inv, via Ctx::inv), or for the whole batch at once in a separate kernel
+// (k_miller prepares, k_fq_inv_batch inverts all norms with one warp-wide Montgomery trick, k_fexp finishes):
+//   prepare:  u_i = conj(dd) t_i (i = 0..2) and the norm nn = |dd|^2 in Fq, where (t0, t1, t2) / dd = N^-1
+//   finish :  f^-1 = conj(f) * ((u0, u1, u2) / nn)
+struct HxInvPrep {
+    Fp2 u0, u1, u2;
+    Fp nn;
+};
 template <class Ctx>
-BN_HD_NOINLINE Fp2 hx_inv(const Ctx c, Fp2 f) {
-    Fp2 fc = hx_conj(c, f);
-    Fp2 n = hx_mul(c, f, fc);  // odd coefficients are zero
+BN_HD_NOINLINE HxInvPrep hx_inv_prepare(const Ctx c, Fp2 f) {
+    Fp2 n = hx_mul(c, f, hx_conj(c, f));  // odd coefficients are zero
     c.sync();
     c.put(0, n);
     c.sync();
@@ -431,13 +532,21 @@ BN_HD_NOINLINE Fp2 hx_inv(const Ctx c, Fp2 f) {
     Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(n2)), fp2_mul(n0, n1));
     Fp2 t2 = fp2_sub(fp2_sqr(n1), fp2_mul(n0, n2));
     Fp2 dd = fp2_add(fp2_mul_xi(fp2_add(fp2_mul(n2, t1), fp2_mul(n1, t2))), fp2_mul(n0, t0));
-    // 1/dd = conj(dd) / (d0^2 + d1^2); the Fq inversion is delegated to the context so a kernel can batch it
-    // (Montgomery's trick over all hexads of a thread block: one Fermat chain per block instead of one per warp)
+    // 1/dd = conj(dd) / (d0^2 + d1^2)
     Wide nn = wide_zero();
     wide_mac2(nn, dd.c0, dd.c0, dd.c1, dd.c1);
-    Fp ninv = c.inv(mont_reduce<MQ, 2>(nn));
-    Fp2 di = Fp2{fp_mul<MQ>(dd.c0, ninv), fp_neg<MQ>(fp_mul<MQ>(dd.c1, ninv))};
-    return hx_mul_fq6(c, fc, fp2_mul(di, t0), fp2_mul(di, t1), fp2_mul(di, t2));
+    const Fp2 dc = fp2_conj(dd);
+    return HxInvPrep{fp2_mul(dc, t0), fp2_mul(dc, t1), fp2_mul(dc, t2), mont_reduce<MQ, 2>(nn)};
+}
+template <class Ctx>
+BN_HD Fp2 hx_inv_finish(const Ctx& c, const Fp2& f, const Fp2& u0, const Fp2& u1, const Fp2& u2, const Fp& ninv) {
+    return hx_mul_fq6(c, hx_conj(c, f), fp2_mul_fp(u0, ninv), fp2_mul_fp(u1, ninv), fp2_mul_fp(u2, ninv));
+}
+template <class Ctx>
+BN_HD_NOINLINE Fp2 hx_inv(const Ctx c, Fp2 f) {
+    const HxInvPrep p = hx_inv_prepare(c, f);
+    // the Fq inversion is delegated to the context so a kernel can batch it (Montgomery's trick over the hexads of a block)
+    return hx_inv_finish(c, f, p.u0, p.u1, p.u2, c.inv(p.nn));
 }
 
 // reference final_exponentiation, src/fields/fq12.rs:41-88: same first chunk, and a last chunk that reaches the same
@@ -448,14 +557,14 @@ BN_HD_NOINLINE Fp2 hx_inv(const Ctx c, Fp2 f) {
 // reference computes   frob3(conj(s) K B) * frob2(K) * frob1(K B) * (s K E).   Frobenius is a ring homomorphism, so this
 // equals   [frob3(conj(s) B) * frob1(B) * s E] * K * frob1(K) * frob2(K) * frob3(K)   : the bracket (C below) and
 // E conj(D) are formed BEFORE the third exponentiation.  Gt elements are canonical, so the bytes are identical.
+// `finv` = f^-1 (hx_inv, or prepared / finished around a batch-wide inversion).
 template <class Ctx>
-BN_HD Fp2 hx_final_exp(const Ctx& c, const Fp2& f) {
+BN_HD Fp2 hx_final_exp_with_inverse(const Ctx& c, const Fp2& f, const Fp2& finv) {
     // first chunk
     Fp2 s;
     {
-        Fp2 b = hx_inv(c, f);
         Fp2 a = hx_conj(c, f);
-        Fp2 cc = hx_mul(c, a, b);
+        Fp2 cc = hx_mul(c, a, finv);
         Fp2 d = hx_frob(c, cc, 2);
         s = hx_mul(c, d, cc);
     }
@@ -480,6 +589,10 @@ BN_HD Fp2 hx_final_exp(const Ctx& c, const Fp2& f) {
     r = hx_mul(c, r, hx_frob(c, kk, 1));
     r = hx_mul(c, r, hx_frob(c, kk, 2));
     return hx_mul(c, r, hx_frob(c, kk, 3));
+}
+template <class Ctx>
+BN_HD Fp2 hx_final_exp(const Ctx& c, const Fp2& f) {
+    return hx_final_exp_with_inverse(c, f, hx_inv(c, f));
 }
 
 // Gt::pow, reference src/fields/mod.rs:35-46 via src/lib.rs:171: 256 squarings, generic (non-cyclotomic).

@@ -77,7 +77,17 @@ __device__ __forceinline__ void st_fp2(uint32_t* p, const Fp2& a) {
 // Shared scratch of a hexad block: one Fq slot per hexad + prefix products for the batched inversion, and the
 // operand-exchange area: per lane three 64-byte slots (a, xi*a / aux, b / aux), lane stride padded to 52 words so the
 // six lanes of a hexad hit disjoint bank groups with 128-bit accesses.
+#if BN_F52
+// FP64 operand exchange (f52.cuh): a slot holds a D5x3 = three 5-double factors at 48-byte pitch (16-byte aligned: two
+// LDS.128 + one LDS.64 each); the integer form of a value (64 bytes, cyclotomic squaring / inversion) uses the first 64
+// bytes of the same slot.  108-word lane stride: 108 mod 32 = 12, so any 8 consecutive lanes hit 8 disjoint 16-byte bank
+// groups.
+#define HEX_SLOT_BYTES 144
+#define HEX_LANE_STRIDE 108
+#else
+#define HEX_SLOT_BYTES 64
 #define HEX_LANE_STRIDE 52
+#endif
 #ifndef BN_LINE_TMA
 #define BN_LINE_TMA 1   // stream the line coefficients HBM -> shared memory with cp.async.bulk (TMA) one step ahead
 #endif
@@ -86,16 +96,19 @@ struct alignas(128) LineRing {
     uint32_t buf[2][HEX_PER_WARP * BN_LINE_WORDS];
     unsigned long long bar[2];
 };
-struct HexSmem {
+struct alignas(128) HexSmem {
     Fp val[HEX_PER_BLOCK];
     Fp pre[HEX_PER_BLOCK];
     alignas(16) uint32_t xch[HEX_WARPS_PER_BLOCK][32 * HEX_LANE_STRIDE];
     alignas(16) uint32_t kq[16 * BN_KQ_STRIDE];  // k*q, k = 0..15 (xi-multiplication reduction rows)
-    alignas(16) uint32_t zero[16];               // an all-zero Fq2: operand "absent" for a lane role, selected by address
-#if BN_LINE_TMA
-    LineRing ring[HEX_WARPS_PER_BLOCK];
-#endif
+    alignas(16) uint32_t zero[HEX_SLOT_BYTES / 4];  // an all-zero operand: "absent" for a lane role, selected by address
 };
+// dynamic shared memory of the hexad kernels: HexSmem | line rings (Miller kernels) | parking area (final exponentiation)
+#if BN_LINE_TMA
+#define HEX_RING_BYTES (HEX_WARPS_PER_BLOCK * sizeof(LineRing))
+#else
+#define HEX_RING_BYTES 0
+#endif
 
 // 1/x for one x per "slot" of a thread block with ONE inversion (Montgomery's simultaneous inversion):
 // prefix products, invert the total, peel back.  Collective over the whole block (two __syncthreads); the chain
@@ -131,6 +144,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void lds128(uint32_t addr, uint32_t* v) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
 }
+__device__ __forceinline__ void lds128d(uint32_t addr, double* v) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+}
+__device__ __forceinline__ void lds64d(uint32_t addr, double* v) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(addr)); }
+__device__ __forceinline__ void sts128d(uint32_t addr, const double* v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v[0]), "d"(v[1]) : "memory");
+}
+__device__ __forceinline__ void sts64d(uint32_t addr, const double* v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v[0]) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
@@ -185,11 +206,29 @@ struct DevCtx {
     }
     __device__ __forceinline__ Fp2 mul_xi(const Fp2& a) const { return fp2_mul_xi_r(a, KqRowLds{kq}); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
-    __device__ __forceinline__ void put(int s, const Fp2& v) const { sts_fp2(mine + s * 64, v); }
-    __device__ __forceinline__ Fp2 get(int src, int s) const { return lds_fp2(hexbase + src * (HEX_LANE_STRIDE * 4) + s * 64); }
+    __device__ __forceinline__ void put(int s, const Fp2& v) const { sts_fp2(mine + s * HEX_SLOT_BYTES, v); }
+    __device__ __forceinline__ Fp2 get(int src, int s) const { return lds_fp2(hexbase + src * (HEX_LANE_STRIDE * 4) + s * HEX_SLOT_BYTES); }
     __device__ __forceinline__ Fp2 get_or_zero(bool cond, int src, int s) const {
-        return lds_fp2(cond ? hexbase + src * (HEX_LANE_STRIDE * 4) + s * 64 : zero);
+        return lds_fp2(cond ? hexbase + src * (HEX_LANE_STRIDE * 4) + s * HEX_SLOT_BYTES : zero);
     }
+#if BN_F52
+    typedef uint32_t Ref;  // shared address of a published D5x3
+    __device__ __forceinline__ void put52(int s, const Fp2& v) const {
+        const D5x3 t = f52_from_fp2(v);
+        const uint32_t a = mine + s * HEX_SLOT_BYTES;
+        sts128d(a, t.c0.l); sts128d(a + 16, t.c0.l + 2); sts64d(a + 32, t.c0.l + 4);
+        sts128d(a + 48, t.c1.l); sts128d(a + 64, t.c1.l + 2); sts64d(a + 80, t.c1.l + 4);
+        sts128d(a + 96, t.cs.l); sts128d(a + 112, t.cs.l + 2); sts64d(a + 128, t.cs.l + 4);
+    }
+    __device__ __forceinline__ Ref ref(int src, int s) const { return hexbase + src * (HEX_LANE_STRIDE * 4) + s * HEX_SLOT_BYTES; }
+    __device__ __forceinline__ Ref ref_or_zero(bool cond, int src, int s) const { return cond ? ref(src, s) : zero; }
+    __device__ __forceinline__ D5 ld5(Ref r, int which) const {
+        D5 v;
+        const uint32_t a = r + which * 48;
+        lds128d(a, v.l); lds128d(a + 16, v.l + 2); lds64d(a + 32, v.l + 4);
+        return v;
+    }
+#endif
     __device__ __forceinline__ Fp small_reduce(const Lazy9& x) const { return lazy_reduce(x, KqRowLds{kq}); }
     __device__ __forceinline__ ModRegs mod_q() const {  // row 1 of the k*q table
         ModRegs r;
@@ -675,7 +714,11 @@ __global__ void __launch_bounds__(DUO_BLOCK) k_pair_lines_duo(const uint32_t* __
 #define HEX_MIN_BLOCKS_POW 1   // the fused pairing.pow kernel keeps four more Gt values live
 #endif
 #define HEX_PARK_WARP_BYTES (HX_PARK_SLOTS * 4 * 32 * 16)
-#define HEX_DYN_SMEM_BYTES (sizeof(HexSmem) + HEX_WARPS_PER_BLOCK * HEX_PARK_WARP_BYTES)
+#define HEX_PARK_BYTES (HEX_WARPS_PER_BLOCK * HEX_PARK_WARP_BYTES)
+#define HEX_SMEM_PLAIN (sizeof(HexSmem))                                   // k_gt_*
+#define HEX_SMEM_MILLER (sizeof(HexSmem) + HEX_RING_BYTES)                 // k_miller
+#define HEX_SMEM_FEXP (sizeof(HexSmem) + HEX_PARK_BYTES)                   // k_fexp, k_fexp_pow, k_fexp_gather
+#define HEX_SMEM_FUSED (sizeof(HexSmem) + HEX_RING_BYTES + HEX_PARK_BYTES) // k_miller_fexp: HexSmem | rings | parking
 extern __shared__ __align__(128) unsigned char hex_dyn_smem[];
 
 struct HexIndex {
@@ -687,10 +730,8 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int hex = lane / 6;  // 0..5 (5 = the two spare lanes)
-    if (threadIdx.x < 16) {
-        kq_table_fill(sm->kq, threadIdx.x);
-        sm->zero[threadIdx.x] = 0;
-    }
+    if (threadIdx.x < 16) kq_table_fill(sm->kq, threadIdx.x);
+    if (threadIdx.x < HEX_SLOT_BYTES / 4) sm->zero[threadIdx.x] = 0;
     __syncthreads();
     HexIndex h;
     h.ctx.kk = lane - hex * 6;
@@ -717,26 +758,26 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
 #define BN_SPLIT_KERNELS 1
 #endif
 #ifndef MILLER_MIN_BLOCKS
-#define MILLER_MIN_BLOCKS 3   // run 28: k_miller 2.31 ms at 3 blocks/SM vs 2.38 ms at 2
+#define MILLER_MIN_BLOCKS 2   // FP64 product path (round 2, run 6): 2.07 ms at 2 blocks/SM (214 registers) vs 2.15 ms at 3 (168); integer path (run 28): 3 was better
 #endif
 #ifndef FEXP_MIN_BLOCKS
 #define FEXP_MIN_BLOCKS 2   // run 28: k_fexp 4.11 ms at 2 blocks/SM (254 registers) vs 4.37 ms at 3 (168 registers, L0 instruction-cache misses)
 #endif
-__device__ __forceinline__ HexIndex hex_index_dyn(size_t n) {
-    // dynamic shared memory: HexSmem, then the parking area (HX_PARK_SLOTS x 64 B per lane, hexad.cuh)
+// dynamic shared memory: HexSmem, then (at park_off) the parking area (HX_PARK_SLOTS x 64 B per lane, hexad.cuh)
+__device__ __forceinline__ HexIndex hex_index_dyn(size_t n, uint32_t park_off = sizeof(HexSmem)) {
     HexSmem* smem = reinterpret_cast<HexSmem*>(hex_dyn_smem);
     HexIndex h = hex_index(n, smem);
-    h.ctx.parkbase = smem_u32(hex_dyn_smem + sizeof(HexSmem)) + (threadIdx.x >> 5) * HEX_PARK_WARP_BYTES + (threadIdx.x & 31) * 16;
+    h.ctx.parkbase = smem_u32(hex_dyn_smem + park_off) + (threadIdx.x >> 5) * HEX_PARK_WARP_BYTES + (threadIdx.x & 31) * 16;
     return h;
 }
 __device__ __forceinline__ Fp2 miller_part(const HexIndex& h, const uint32_t* __restrict__ lines, size_t n, uint32_t* err) {
 #if BN_LINE_TMA
-    HexSmem* smem = reinterpret_cast<HexSmem*>(hex_dyn_smem);
+    LineRing* rings = reinterpret_cast<LineRing*>(hex_dyn_smem + sizeof(HexSmem));  // right after HexSmem (128-byte aligned)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     size_t p0 = ((size_t)blockIdx.x * HEX_WARPS_PER_BLOCK + warp) * HEX_PER_WARP;
     if (p0 >= n) p0 = n >= HEX_PER_WARP ? n - HEX_PER_WARP : 0;  // warp with no real pairing: any valid rows will do
     const int hex = lane / 6;
-    DevLineSrcTma src{lines + p0 * BN_LINE_WORDS, n * (size_t)BN_LINE_WORDS, smem_u32(&smem->ring[warp]),
+    DevLineSrcTma src{lines + p0 * BN_LINE_WORDS, n * (size_t)BN_LINE_WORDS, smem_u32(&rings[warp]),
                       (uint32_t)((hex < HEX_PER_WARP ? hex : HEX_PER_WARP - 1) * BN_LINE_WORDS * 4),
                       (uint32_t)(4 * BN_LINE_OFF_L0) | ((uint32_t)(4 * (h.ctx.kk < 3 ? BN_LINE_OFF_XL3 : BN_LINE_OFF_L3)) << 10) |
                           ((uint32_t)(4 * (h.ctx.kk < 4 ? BN_LINE_OFF_XL4 : BN_LINE_OFF_L4)) << 20),
@@ -747,9 +788,18 @@ __device__ __forceinline__ Fp2 miller_part(const HexIndex& h, const uint32_t* __
 #endif
     return hx_miller_loop(h.ctx, src);
 }
-template <bool POW>
-__device__ __forceinline__ Fp2 fexp_part(const HexIndex& h, Fp2 f, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k) {
-    f = hx_final_exp(h.ctx, f);
+// INV_BATCHED: f^-1 is finished from what k_miller prepared (aux: u0, u1, u2) and k_fq_inv_batch inverted (ninv);
+// otherwise the whole inversion happens here, the Fq inversion batched over the block (Ctx::inv).
+template <bool POW, bool INV_BATCHED>
+__device__ __forceinline__ Fp2 fexp_part(const HexIndex& h, Fp2 f, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k,
+                                         const uint32_t* __restrict__ aux, const uint32_t* __restrict__ ninv) {
+    if (INV_BATCHED) {
+        const uint32_t* a = aux + h.pidx * 48;
+        const Fp2 finv = hx_inv_finish(h.ctx, f, ld_fp2(a), ld_fp2(a + 16), ld_fp2(a + 32), ld_fp(ninv + h.pidx * 8));
+        f = hx_final_exp_with_inverse(h.ctx, f, finv);
+    } else {
+        f = hx_final_exp(h.ctx, f);
+    }
     if (!flags[h.pidx]) f = hx_one(h.ctx);  // infinity => Gt::one(), reference src/groups/mod.rs:765-766
     if (POW) {
         Fp e = fp_from_mont<ModR>(ld_fp(k + h.pidx * 8));  // U256::from(Fr), reference src/fields/fp.rs:15-22
@@ -758,23 +808,72 @@ __device__ __forceinline__ Fp2 fexp_part(const HexIndex& h, Fp2 f, const uint8_t
     return f;
 }
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, MILLER_MIN_BLOCKS)
-k_miller(const uint32_t* __restrict__ lines, uint32_t* __restrict__ out, size_t n, uint32_t* err) {
+k_miller(const uint32_t* __restrict__ lines, uint32_t* __restrict__ out, size_t n, uint32_t* err, uint32_t* __restrict__ aux,
+         uint32_t* __restrict__ norm) {
     HexIndex h = hex_index_dyn(n);
     Fp2 f = miller_part(h, lines, n, err);
     if (h.active) st_fp2(out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk), f);
+    // first half of the final exponentiation's Fq12 inversion (hexad.cuh hx_inv_prepare): everything down to the one Fq
+    // element per pairing that must be inverted.  All six lanes hold the same values; lanes 0..2 store u_k, lane 3 the norm.
+    const HxInvPrep p = hx_inv_prepare(h.ctx, f);
+    if (h.active) {
+        const int kk = h.ctx.kk;
+        if (kk < 3) st_fp2(aux + h.pidx * 48 + kk * 16, kk == 0 ? p.u0 : (kk == 1 ? p.u1 : p.u2));
+        if (kk == 3) st_fp(norm + h.pidx * 8, p.nn);
+    }
+}
+
+// v[i] <- v[i]^-1 (Montgomery form, mod q) for n values, one value per lane: a warp multiplies its 32 values together with
+// a log-step prefix and suffix product scan (10 Fq multiplications of latency instead of 93), ONE lane inverts the total
+// (binary Euclid, fp2.cuh: data-dependent loops run on a single lane), and every lane recovers its own inverse as
+// total^-1 * prefix[i-1] * suffix[i+1].  Zero (only the padding / infinity pairs, whose results are discarded) counts as 1.
+// Replaces the per-block single-thread inversion inside k_fexp, during which the block's four warps sat at a barrier
+// (10 % of that kernel, profiles/r02_run5): 16 384 inversions cost one ~25 k-instruction Euclid chain of latency, once.
+__global__ void __launch_bounds__(128) k_fq_inv_batch(uint32_t* __restrict__ v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Fp x = fq_one();
+    if (i < n) {
+        x = ld_fp_rw(v + i * 8);
+        if (fp_is_zero(x)) x = fq_one();
+    }
+    auto shfl_fp = [](const Fp& a, int src) {
+        Fp r;
+#pragma unroll
+        for (int l = 0; l < 8; l++) r.v[l] = __shfl_sync(0xffffffffu, a.v[l], src);
+        return r;
+    };
+    // inclusive scans: pre[i] = x_0 ... x_i, suf[i] = x_i ... x_31
+    Fp pre = x, suf = x;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const Fp a = shfl_fp(pre, lane - d < 0 ? lane : lane - d), b = shfl_fp(suf, lane + d > 31 ? lane : lane + d);
+        const Fp pa = fp_mul_ni<MQ>(pre, a), sb = fp_mul_ni<MQ>(suf, b);
+        if (lane - d >= 0) pre = pa;
+        if (lane + d <= 31) suf = sb;
+    }
+    Fp tinv = fq_one();
+    if (lane == 31) tinv = fq_inv_euclid(pre);
+    tinv = shfl_fp(tinv, 31);
+    const Fp left = shfl_fp(pre, lane == 0 ? 0 : lane - 1), right = shfl_fp(suf, lane == 31 ? 31 : lane + 1);
+    Fp r = tinv;
+    if (lane > 0) r = fp_mul_ni<MQ>(r, left);
+    if (lane < 31) r = fp_mul_ni<MQ>(r, right);
+    if (i < n) st_fp(v + i * 8, r);
 }
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, FEXP_MIN_BLOCKS)
-k_fexp(const uint8_t* __restrict__ flags, uint32_t* out, size_t n) {
+k_fexp(const uint8_t* __restrict__ flags, uint32_t* out, size_t n, const uint32_t* __restrict__ aux, const uint32_t* __restrict__ ninv) {
     HexIndex h = hex_index_dyn(n);
     uint32_t* p = out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk);
-    Fp2 f = fexp_part<false>(h, ld_fp2_rw(p), flags, nullptr);
+    Fp2 f = fexp_part<false, true>(h, ld_fp2_rw(p), flags, nullptr, aux, ninv);
     if (h.active) st_fp2(p, f);
 }
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS_POW)
-k_fexp_pow(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k, uint32_t* out, size_t n) {
+k_fexp_pow(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ k, uint32_t* out, size_t n, const uint32_t* __restrict__ aux,
+           const uint32_t* __restrict__ ninv) {
     HexIndex h = hex_index_dyn(n);
     uint32_t* p = out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk);
-    Fp2 f = fexp_part<true>(h, ld_fp2_rw(p), flags, k);
+    Fp2 f = fexp_part<true, true>(h, ld_fp2_rw(p), flags, k, aux, ninv);
     if (h.active) st_fp2(p, f);
 }
 // Final exponentiation fused with the multi-GPU gather: the epilogue stores each result straight
@@ -785,25 +884,25 @@ struct PeerOut {
     uint32_t* slot[BN_MAX_PEERS];  // slot[r] = peer r's gather buffer + this rank's offset
 };
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, FEXP_MIN_BLOCKS)
-k_fexp_gather(const uint8_t* __restrict__ flags, const uint32_t* out, PeerOut peers, int world, size_t n) {
+k_fexp_gather(const uint8_t* __restrict__ flags, const uint32_t* out, PeerOut peers, int world, size_t n, const uint32_t* __restrict__ aux,
+              const uint32_t* __restrict__ ninv) {
     HexIndex h = hex_index_dyn(n);
     const size_t off = h.pidx * 96 + 16 * gt_slot(h.ctx.kk);  // `out` may alias peers.slot[rank]: coherent loads, no __restrict__
-    Fp2 f = fexp_part<false>(h, ld_fp2_rw(out + off), flags, nullptr);
+    Fp2 f = fexp_part<false, true>(h, ld_fp2_rw(out + off), flags, nullptr, aux, ninv);
     if (h.active)
         for (int r = 0; r < world; r++) st_fp2(peers.slot[r] + off, f);
 }
 // fused single-kernel form (A/B: BN_SPLIT_KERNELS=0)
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK, HEX_MIN_BLOCKS)
 k_miller_fexp(const uint32_t* __restrict__ lines, const uint8_t* __restrict__ flags, uint32_t* __restrict__ out, size_t n, uint32_t* err) {
-    HexIndex h = hex_index_dyn(n);
-    Fp2 f = fexp_part<false>(h, miller_part(h, lines, n, err), flags, nullptr);
+    HexIndex h = hex_index_dyn(n, sizeof(HexSmem) + HEX_RING_BYTES);
+    Fp2 f = fexp_part<false, false>(h, miller_part(h, lines, n, err), flags, nullptr, nullptr, nullptr);
     if (h.active) st_fp2(out + h.pidx * 96 + 16 * gt_slot(h.ctx.kk), f);
 }
 
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
 k_gt_mul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n) {
-    __shared__ HexSmem smem;
-    HexIndex h = hex_index(n, &smem);
+    HexIndex h = hex_index(n, reinterpret_cast<HexSmem*>(hex_dyn_smem));
     const int slot = 16 * gt_slot(h.ctx.kk);
     Fp2 x = ld_fp2(a + h.pidx * 96 + slot), y = ld_fp2(b + h.pidx * 96 + slot);
     Fp2 r = hx_mul(h.ctx, x, y);
@@ -813,8 +912,7 @@ k_gt_mul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_
 // Gt::inverse (reference src/lib.rs:172 -> Fq12::inverse, src/fields/fq12.rs:284-292); b is unused.
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
 k_gt_inv(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n) {
-    __shared__ HexSmem smem;
-    HexIndex h = hex_index(n, &smem);
+    HexIndex h = hex_index(n, reinterpret_cast<HexSmem*>(hex_dyn_smem));
     const int slot = 16 * gt_slot(h.ctx.kk);
     Fp2 x = ld_fp2(a + h.pidx * 96 + slot);
     Fp2 r = hx_inv(h.ctx, x);
@@ -826,8 +924,7 @@ k_gt_inv(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_
 // reference's test_cyclotomic_exp pins (src/fields/mod.rs:171-201, a non-cyclotomic input).  b is unused.
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
 k_gt_exp_neg_z(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* __restrict__ out, size_t n) {
-    __shared__ HexSmem smem;
-    HexIndex h = hex_index(n, &smem);
+    HexIndex h = hex_index(n, reinterpret_cast<HexSmem*>(hex_dyn_smem));
     const int slot = 16 * gt_slot(h.ctx.kk);
     Fp2 x = ld_fp2(a + h.pidx * 96 + slot);
     Fp2 r = hx_exp_by_neg_z_literal(h.ctx, x);
@@ -836,8 +933,7 @@ k_gt_exp_neg_z(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, u
 
 __global__ void __launch_bounds__(32 * HEX_WARPS_PER_BLOCK)
 k_gt_pow(const uint32_t* __restrict__ a, const uint32_t* __restrict__ k, uint32_t* __restrict__ out, size_t n) {
-    __shared__ HexSmem smem;
-    HexIndex h = hex_index(n, &smem);
+    HexIndex h = hex_index(n, reinterpret_cast<HexSmem*>(hex_dyn_smem));
     const int slot = 16 * gt_slot(h.ctx.kk);
     Fp2 x = ld_fp2(a + h.pidx * 96 + slot);
     Fp e = fp_from_mont<ModR>(ld_fp(k + h.pidx * 8));  // U256::from(Fr), reference src/fields/fp.rs:15-22

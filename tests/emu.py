@@ -20,7 +20,8 @@ def lib(variant: str = "product"):
         deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".inc"))]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             flags = os.environ.get("BN_EMU_FLAGS", "").split() + ([] if variant == "product" else ["-DBN_ATE_NAF=0"])
-            subprocess.check_call(["g++", "-O2", "-std=c++17", *flags, "-shared", "-fPIC", "-o", so, src, "-lpthread"])
+            # -frounding-math / -mfma: f52.cuh's round-toward-zero fma runs under fesetround(FE_TOWARDZERO) on the host
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-frounding-math", "-mfma", *flags, "-shared", "-fPIC", "-o", so, src, "-lpthread"])
         _libs[variant] = ctypes.CDLL(so)
     return _libs[variant]
 
@@ -37,6 +38,14 @@ def fp_op(op, which, a, b=None):
     a, b = _c(a), _c(b)
     out = np.zeros(4, dtype=np.uint64)
     lib().emu_fp_op(op, which, _p(a), _p(b), _p(out))
+    return out
+
+
+def f52_mul(a, b):
+    """a * b * 2^-256 mod q through the FP64 product path (f52.cuh)."""
+    a, b = _c(a), _c(b)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().emu_f52_mul(_p(a), _p(b), _p(out))
     return out
 
 

@@ -6,6 +6,7 @@
 // against the oracle, so the tower / lane choreography / line schedule is validated without a GPU;
 // the -m gpu tests then validate the real kernels (PTX included) through the C ABI.
 #include <atomic>
+#include <cfenv>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -35,6 +36,7 @@ struct Barrier {
 
 struct HostHexShared {
     Fp2 slot[6][3];
+    D5x3 slot52[6][3];
     Fp2 parked[6][HX_PARK_SLOTS];
     Barrier bar{6};
 };
@@ -60,6 +62,15 @@ struct HostCtx {
     Fp small_reduce(const Lazy9& x) const { return lazy_reduce(x, KqRowPtr{kq_tab()}); }
     Fp2 get_or_zero(bool cond, int src, int s) const { return cond ? sh->slot[src][s] : fp2_zero(); }
     void put(int s, const Fp2& v) const { sh->slot[kk][s] = v; }
+    // FP64 operand exchange (f52.cuh): Ref = pointer to a published D5x3 (nullptr: the zero operand)
+    typedef const D5x3* Ref;
+    void put52(int s, const Fp2& v) const { sh->slot52[kk][s] = f52_from_fp2(v); }
+    Ref ref(int src, int s) const { return &sh->slot52[src][s]; }
+    Ref ref_or_zero(bool cond, int src, int s) const { return cond ? &sh->slot52[src][s] : nullptr; }
+    D5 ld5(Ref r, int which) const {
+        if (!r) return D5{{0.0, 0.0, 0.0, 0.0, 0.0}};
+        return which == 0 ? r->c0 : (which == 1 ? r->c1 : r->cs);
+    }
     Fp2 get(int src, int s) const { return sh->slot[src][s]; }
     void sync() const { sh->bar.wait(); }
     void park(int s, const Fp2& v) const { sh->parked[kk][s] = v; }
@@ -111,7 +122,12 @@ template <class Fn>
 void run_hexad(Fn fn) {
     HostHexShared sh;
     std::vector<std::thread> th;
-    for (int k = 0; k < 6; k++) th.emplace_back([&sh, k, &fn]() { HostCtx c{k, &sh}; fn(c); });
+    for (int k = 0; k < 6; k++)
+        th.emplace_back([&sh, k, &fn]() {
+            std::fesetround(FE_TOWARDZERO);  // f52.cuh's fma_rz on the host: the FPU rounding mode is per thread
+            HostCtx c{k, &sh};
+            fn(c);
+        });
     for (auto& t : th) t.join();
 }
 
@@ -162,6 +178,7 @@ void emu_fp_op(int op, int which, const uint64_t* a, const uint64_t* b, uint64_t
             case 4: r = fp_inv<ModQ>(x); break;
             case 5: r = fp_half<ModQ>(x); break;
             case 7: r = fq_inv_euclid(x); break;
+            case 8: r = fp_sqr<ModQ>(x); break;
             default: r = fp_from_mont<ModQ>(x); break;
         }
     } else {
@@ -172,11 +189,20 @@ void emu_fp_op(int op, int which, const uint64_t* a, const uint64_t* b, uint64_t
             case 3: r = fp_neg<ModR>(x); break;
             case 4: r = fp_inv<ModR>(x); break;
             case 5: r = fp_half<ModR>(x); break;
+            case 8: r = fp_sqr<ModR>(x); break;
             default: r = fp_from_mont<ModR>(x); break;
         }
     }
     store_fp(out, r);
 }
+// a * b * 2^-256 mod q through the FP64 path (f52.cuh), to be compared with emu_fp_op(0, 0, ...)
+void emu_f52_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    const int old = std::fegetround();
+    std::fesetround(FE_TOWARDZERO);
+    store_fp(out, f52_fp_mul(load_fp(a), load_fp(b)));
+    std::fesetround(old);
+}
+int emu_f52_enabled() { return BN_F52; }
 // op: 0 mul, 1 sqr, 2 mul_xi, 3 inv, 4 add, 5 sub
 void emu_fp2_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
     Fp2 x = load_fp2(a), y = b ? load_fp2(b) : fp2_zero(), r;

@@ -191,3 +191,29 @@ def test_hexad_ops_extreme_coefficients():
         assert np.array_equal(emu.gt_op(1, xi), util.gt_img(o.fq12_sqr(x))), ("sqr", i)
         y = elems[(i + 3) % len(elems)]
         assert np.array_equal(emu.gt_op(0, xi, util.gt_img(y)), util.gt_img(o.fq12_mul(x, y))), ("mul", i)
+
+
+def test_f52_product_path_matches_integer_path():
+    """f52.cuh (5 x 52-bit limbs on the FP64 pipe, Montgomery radix 2^256 by 4 x 52 + 48 bit rounds) against the oracle's
+    Montgomery product, extremes included."""
+    import random
+    rng = random.Random(52)
+    vals = [0, 1, 2, o.Q - 1, o.Q - 2, (1 << 254) % o.Q, (1 << 52) - 1, 1 << 52, (1 << 208) + 1, o.Q // 2]
+    vals += [rng.randrange(o.Q) for _ in range(60)]
+    rinv = pow(1 << 256, -1, o.Q)
+    w = lambda v: util.words(v.to_bytes(32, "little"))
+    for i, a in enumerate(vals):
+        for b in (vals[(3 * i + 1) % len(vals)], vals[(7 * i + 5) % len(vals)], a):
+            got = emu.f52_mul(w(a), w(b))
+            assert int.from_bytes(got.tobytes(), "little") == a * b * rinv % o.Q, (a, b)
+
+
+def test_dedicated_squaring_matches_multiplication():
+    """fp_sqr (36-IMAD triangle + diagonal, fp.cuh wide_sqr) == fp_mul(a, a) for Fq and Fr, extremes included."""
+    import random
+    rng = random.Random(108)
+    for which, mod in ((0, o.Q), (1, o.R_ORDER)):
+        vals = [0, 1, 2, mod - 1, mod - 2, (1 << 253) % mod, (1 << 32) - 1, (1 << 224) + (1 << 32) - 1, mod // 2] + [rng.randrange(mod) for _ in range(100)]
+        for v in vals:
+            w = util.words(v.to_bytes(32, "little"))
+            assert np.array_equal(emu.fp_op(8, which, w), emu.fp_op(0, which, w, w)), (which, v)
