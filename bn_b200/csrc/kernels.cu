@@ -425,12 +425,14 @@ template <>
 struct JacIO<FqOps> {
     static constexpr int WORDS = 24;
     static __device__ __forceinline__ Jac<FqOps> ld(const uint32_t* p) { return Jac<FqOps>{ld_fp(p), ld_fp(p + 8), ld_fp(p + 16)}; }
+    static __device__ __forceinline__ Jac<FqOps> ld_s(const uint32_t* p) { return Jac<FqOps>{ld_fp_rw(p), ld_fp_rw(p + 8), ld_fp_rw(p + 16)}; }
     static __device__ __forceinline__ void st(uint32_t* p, const Jac<FqOps>& a) { st_fp(p, a.x); st_fp(p + 8, a.y); st_fp(p + 16, a.z); }
 };
 template <>
 struct JacIO<Fq2Ops> {
     static constexpr int WORDS = 48;
     static __device__ __forceinline__ Jac<Fq2Ops> ld(const uint32_t* p) { return Jac<Fq2Ops>{ld_fp2(p), ld_fp2(p + 16), ld_fp2(p + 32)}; }
+    static __device__ __forceinline__ Jac<Fq2Ops> ld_s(const uint32_t* p) { return Jac<Fq2Ops>{ld_fp2_rw(p), ld_fp2_rw(p + 16), ld_fp2_rw(p + 32)}; }
     static __device__ __forceinline__ void st(uint32_t* p, const Jac<Fq2Ops>& a) { st_fp2(p, a.x); st_fp2(p + 16, a.y); st_fp2(p + 32, a.z); }
 };
 template <class F>
@@ -460,6 +462,79 @@ __global__ void __launch_bounds__(128) k_g1_eq(const uint32_t* __restrict__ a, c
 __global__ void __launch_bounds__(128) k_g2_eq(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint8_t* __restrict__ out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = jac_eq<Fq2Ops>(JacIO<Fq2Ops>::ld(a + i * 48), JacIO<Fq2Ops>::ld(b + i * 48)) ? 1 : 0;
+}
+
+// ---- scalar multiplication with block-wide compaction of the additions (BASELINE config 3) ----------------------------
+// The reference's chain (double every step, add on set bits; src/groups/mod.rs:250-270) is kept operation for operation so
+// the Jacobian limbs match, but the ADDITIONS of one bit position are gathered over the whole thread block: the threads
+// whose scalar has the bit set park their running point in shared memory, the first c threads of the block (c = number of
+// set bits, about half) each perform one addition, and the owners read their result back.  Whole warps above c skip the
+// 16-multiplication addition instead of executing it with half of their lanes masked off (one thread per point with
+// per-lane branches costs 7 + 16 multiplications per step and warp; compacted, 7 + 16 * ceil(c / 32) / warps ~ 7 + 9).
+#define GMUL_THREADS_G1 256
+#define GMUL_THREADS_G2 128
+template <class F, int THREADS>
+__device__ __forceinline__ void g_mul_compact(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k, uint32_t* __restrict__ out,
+                                              size_t n, uint32_t* smem) {
+    typedef JacIO<F> IO;
+    constexpr int WORDS = IO::WORDS, NW = THREADS / 32;
+    uint32_t* pbuf = smem;                                  // [THREADS][WORDS]: every thread's base point
+    uint32_t* rbuf = smem + THREADS * WORDS;                // [THREADS][WORDS]: running points handed to the adders
+    uint32_t* list = rbuf + THREADS * WORDS;                // [THREADS]: owners of the compacted additions
+    uint32_t* wcount = list + THREADS;                      // [NW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t i = (size_t)blockIdx.x * THREADS + tid;
+    const bool active = i < n;
+    const size_t ii = active ? i : n - 1;
+    IO::st(pbuf + tid * WORDS, IO::ld(p + ii * WORDS));
+    const Fp sc = fp_from_mont<ModR>(ld_fp(k + ii * 8));  // U256::from(Fr), reference src/fields/fp.rs:15-22
+    Jac<F> res;
+    res.x = F::zero();
+    res.y = F::one();
+    res.z = F::zero();  // G::zero(), reference src/groups/mod.rs:208-214
+    bool found_one = false;
+    for (int w = 7; w >= 0; w--) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int l = 0; l < 8; l++) bits = (w == l) ? sc.v[l] : bits;
+        for (int b = 31; b >= 0; b--) {
+            if (found_one) res = jac_double<F>(res);
+            const bool add = active && ((bits >> b) & 1u);
+            const uint32_t m = __ballot_sync(0xffffffffu, add);
+            if (lane == 0) wcount[warp] = __popc(m);
+            __syncthreads();
+            int base = 0, total = 0;
+#pragma unroll
+            for (int x = 0; x < NW; x++) {
+                const int cx = (int)wcount[x];
+                base += x < warp ? cx : 0;
+                total += cx;
+            }
+            if (add) {
+                list[base + __popc(m & ((1u << lane) - 1u))] = tid;
+                IO::st(rbuf + tid * WORDS, res);
+                found_one = true;
+            }
+            __syncthreads();
+            if (tid < total) {  // whole warps beyond `total` skip the addition
+                const int j = (int)list[tid];
+                IO::st(rbuf + j * WORDS, jac_add<F>(IO::ld_s(rbuf + j * WORDS), IO::ld_s(pbuf + j * WORDS)));
+            }
+            __syncthreads();
+            if (add) res = IO::ld_s(rbuf + tid * WORDS);
+        }
+    }
+    if (active) IO::st(out + i * WORDS, res);
+}
+extern __shared__ __align__(16) uint32_t gmul_smem[];
+#define GMUL_SMEM(F_WORDS, THREADS) ((size_t)(2 * (THREADS) * (F_WORDS) + (THREADS) + (THREADS) / 32) * 4)
+__global__ void __launch_bounds__(GMUL_THREADS_G1, 2) k_g1_mul_c(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k,
+                                                              uint32_t* __restrict__ out, size_t n) {
+    g_mul_compact<FqOps, GMUL_THREADS_G1>(p, k, out, n, gmul_smem);
+}
+__global__ void __launch_bounds__(GMUL_THREADS_G2) k_g2_mul_c(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k,
+                                                              uint32_t* __restrict__ out, size_t n) {
+    g_mul_compact<Fq2Ops, GMUL_THREADS_G2>(p, k, out, n, gmul_smem);
 }
 
 // Fr::pow(self, exp: Fr) (reference src/lib.rs:24 -> FieldElement::pow, src/fields/mod.rs:35-46: the exponent is
