@@ -233,15 +233,21 @@ def build_roofline(m, clocks):
     traffic = None
     if dominant in ncu_k and fresh:
         traffic = ncu_k[dominant]["dram_read_bytes"] + ncu_k[dominant]["dram_write_bytes"]
-    # Issue-slot model: a warp instruction costs ~4 issue cycles (IMAD.WIDE) or ~1.77 (others).
+    # Pipe model (tools/ubench/pipes2.cu): scheduler cycles per warp instruction are 4.1 for
+    # IMAD.WIDE (fmaheavy), 2.19 for DFMA/DADD (FP64 pipe), 2.0 for ALU-pipe integer instructions; the pipes run
+    # concurrently, so the bound of a launch is the busiest pipe.  Instruction counts: ncu source page of THIS build.
     sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
     slot = {}
     for k, v in ncu_k.items():
         if k in kern and "inst_imad_wide" in v and fresh:
-            cyc = (4.0 * v["inst_imad_wide"] + 1.77 * (v["inst_total"] - v["inst_imad_wide"])) / (m.get("sm_count", 148) * 4)
-            bound_ms = cyc / (sm_mhz * 1e3) * (n / v.get("pairs", n))
-            slot[k] = {"bound_ms": bound_ms, "measured_ms": kern[k][0], "frac": bound_ms / kern[k][0],
-                       "imad_wide_share": v["inst_imad_wide"] / v["inst_total"]}
+            smsp = m.get("sm_count", 148) * 4
+            scale = (n / v.get("pairs", n)) / smsp / (sm_mhz * 1e3)
+            pipes = {"fmaheavy_imad_wide": 4.1 * v["inst_imad_wide"] * scale, "fp64": 2.19 * v.get("inst_fp64", 0) * scale,
+                     "alu": 2.0 * v.get("inst_alu", 0) * scale}
+            bound_ms = max(pipes.values())
+            slot[k] = {"bound_ms": bound_ms, "busiest_pipe": max(pipes, key=pipes.get), "pipe_ms": pipes, "measured_ms": kern[k][0],
+                       "frac": bound_ms / kern[k][0], "inst_total": v["inst_total"],
+                       "issue_active_pct": v.get("smsp__issue_active.avg.pct_of_peak_sustained_active")}
     total_ms = sum(v[0] for v in kern.values())
     line_bytes = m.get("line_bytes_per_pairing", 0)
     r = {
@@ -258,7 +264,7 @@ def build_roofline(m, clocks):
         "kernels": {k: {"ms": v[0], "achieved_timad": n / (v[0] * 1e-3) * v[1] * IMAD_PER_M / 1e12,
                         "frac": n / (v[0] * 1e-3) * v[1] * IMAD_PER_M / imad_peak} for k, v in kern.items()},
         "whole_path_frac": (n / (total_ms * 1e-3)) * M_PAIRING * IMAD_PER_M / imad_peak,
-        "issue_slot_model": slot or None,
+        "pipe_model": slot or None,
         "ncu_artefact": {"file": "profiles/ncu_kernels.json", "capture": ncu.get("source"), "matches_this_build": fresh},
         "traffic_detail": {"algorithmic_bytes_per_pairing": BYTES_IN + BYTES_OUT, "scratch_bytes_per_pairing": line_bytes,
                            "ncu": {k: {"dram_read_bytes": v.get("dram_read_bytes"), "dram_write_bytes": v.get("dram_write_bytes")}

@@ -33,6 +33,16 @@
 #define BN_F52 1   // 1: Fq2 multiply-accumulate + reduction on the FP64 pipe (f52.cuh); 0: IMAD.WIDE accumulators (A/B)
 #endif
 #include "f52.cuh"
+// per-operation A/B switches of the product path (all default to BN_F52)
+#ifndef BN_F52_LINE
+#define BN_F52_LINE BN_F52
+#endif
+#ifndef BN_F52_CYC
+#define BN_F52_CYC BN_F52
+#endif
+#ifndef BN_F52_SQR
+#define BN_F52_SQR BN_F52
+#endif
 
 namespace bn {
 
@@ -41,11 +51,24 @@ namespace bn {
 // one 144-byte slot) with c.put52, and the receivers name a published operand by a Ctx::Ref (c.ref(lane, slot) /
 // c.ref_or_zero(cond, lane, slot)) and load one factor at a time (c.ld5(ref, which)), so that only 2 x 5 doubles are live
 // next to the column accumulators.
+#ifndef BN_F52_PREFETCH
+#define BN_F52_PREFETCH 0   // 1: issue the loads of the next factor pair before the current product's arithmetic (+20 registers)
+#endif
 template <class Ctx>
 BN_HD void mac52_rr(const Ctx& c, Acc52& A, typename Ctx::Ref x, typename Ctx::Ref y) {
+#if BN_F52_PREFETCH
+    D5 a0 = c.ld5(x, 0), b0 = c.ld5(y, 0);
+    D5 a1 = c.ld5(x, 1), b1 = c.ld5(y, 1);
+    f52_mac(A.s0, a0, b0);
+    a0 = c.ld5(x, 2);
+    b0 = c.ld5(y, 2);
+    f52_mac(A.s1, a1, b1);
+    f52_mac(A.s2, a0, b0);
+#else
     f52_mac(A.s0, c.ld5(x, 0), c.ld5(y, 0));
     f52_mac(A.s1, c.ld5(x, 1), c.ld5(y, 1));
     f52_mac(A.s2, c.ld5(x, 2), c.ld5(y, 2));
+#endif
 }
 template <class Ctx>
 BN_HD void mac52_rv(const Ctx& c, Acc52& A, typename Ctx::Ref x, const D5x3& y) {
@@ -269,7 +292,7 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
     {
         Fp2 xa = c.mul_xi(a);
         c.sync();
-#if BN_F52
+#if BN_F52_SQR
         c.put52(0, a);
         c.put52(1, xa);
         c.put52(2, fp2_dbl(fp2_select(k >= 4, xa, a)));
@@ -280,7 +303,7 @@ BN_HD_NOINLINE Fp2 hx_sqr(const Ctx c, Fp2 a) {
 #endif
         c.sync();
     }
-#if BN_F52
+#if BN_F52_SQR
     Acc52 acc;
     acc52_init(acc);
 #else
@@ -301,7 +324,7 @@ BN_UNROLL_N(BN_SQR_UNROLL)
         const int xsrc = nib(xs, k);
         // slot: doubled (2) in rounds 0-1 and for sources 3,4 in round 2; plain (0) otherwise in round 2; xi (1) in round 3
         const int xslot = r < 2 ? 2 : (r == 2 ? ((xsrc == 3 || xsrc == 4) ? 2 : 0) : 1);
-#if BN_F52
+#if BN_F52_SQR
         mac52_rr(c, acc, c.ref(xsrc, xslot), c.ref_or_zero(!(r == 3 && (k & 1) != 0), nib(ys, k), 0));
 #else
         Fp2 x = c.get(xsrc, xslot);
@@ -309,7 +332,7 @@ BN_UNROLL_N(BN_SQR_UNROLL)
         mac_fp2(acc, x, y);
 #endif
     }
-#if BN_F52
+#if BN_F52_SQR
     return acc52_reduce<4>(acc);
 #else
     return reduce2(acc);
@@ -324,7 +347,7 @@ template <class Ctx, class LineSrc>
 BN_HD_NOINLINE Fp2 hx_mul_line(const Ctx c, Fp2 a, const LineSrc src, typename LineSrc::Handle h) {
     const int k = c.k();
     c.sync();
-#if BN_F52
+#if BN_F52_LINE
     c.put52(0, a);
     c.sync();
     Acc52 acc;
@@ -433,7 +456,7 @@ BN_HD_NOINLINE Fp2 hx_cyc_sqr(const Ctx c, Fp2 a) {
         f1.c0 = fp_add_raw(f1.c0, v.c0);
         f1.c1 = fp_add_raw(f1.c1, v.c1);
     }
-#if BN_F52
+#if BN_F52_CYC
     Acc52 acc;
     acc52_init(acc);
     acc52_mac(acc, f52_from_fp2(f0), f52_from_fp2(f1));  // components < 2q, their sums < 4q < 2^256

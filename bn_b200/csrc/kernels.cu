@@ -806,7 +806,7 @@ __device__ __forceinline__ HexIndex hex_index(size_t n, HexSmem* sm) {
     const int warp = threadIdx.x >> 5;
     const int hex = lane / 6;  // 0..5 (5 = the two spare lanes)
     if (threadIdx.x < 16) kq_table_fill(sm->kq, threadIdx.x);
-    if (threadIdx.x < HEX_SLOT_BYTES / 4) sm->zero[threadIdx.x] = 0;
+    for (int z = threadIdx.x; z < HEX_SLOT_BYTES / 4; z += blockDim.x) sm->zero[z] = 0;
     __syncthreads();
     HexIndex h;
     h.ctx.kk = lane - hex * 6;

@@ -16,7 +16,7 @@ def measurements(**over):
          "gather_mode": "fused", "num_lines": 88, "sm_count": 148, "imad_peak": 9.26e12,
          "kernels": {"k_pair_lines_duo": (1.57, bench.M_LINES), "k_miller": (2.18, bench.M_MILLER), "k_fexp": (3.77, bench.M_FEXP)},
          "e2e_value": 1.5e7,
-         "ncu": {"source": "x", "source_hash": "abc", "kernels": {"k_fexp": {"inst_total": 10, "inst_imad_wide": 3, "pairs": 16384,
+         "ncu": {"source": "x", "source_hash": "abc", "kernels": {"k_fexp": {"inst_total": 10, "inst_imad_wide": 3, "inst_fp64": 4, "inst_alu": 3, "pairs": 16384,
                                                                                  "dram_read_bytes": 1, "dram_write_bytes": 2}}},
          "source_hash": "abc"}
     m.update(over)
@@ -29,7 +29,7 @@ def test_report_with_unsampled_clocks():
         line = bench.build_line(measurements(clocks=clocks))
         json.dumps(line)
         assert line["value"] == 1.6e7 and line["n_gpus"] == 8 and "roofline" in line and "roofline_error" not in line
-        assert line["roofline"]["issue_slot_model"]["k_fexp"]["bound_ms"] > 0
+        assert line["roofline"]["pipe_model"]["k_fexp"]["bound_ms"] > 0
         assert line["config"]["global_pairs"] == 8 * 16384
 
 
@@ -38,7 +38,7 @@ def test_report_without_optional_legs():
     for k in ("ncu", "source_hash", "e2e_value"):
         m.pop(k)
     line = bench.build_line(m)
-    assert "e2e" not in line and line["roofline"]["traffic"] is None and line["roofline"]["issue_slot_model"] is None
+    assert "e2e" not in line and line["roofline"]["traffic"] is None and line["roofline"]["pipe_model"] is None
     # a stale ncu artefact (other build) is not used
     line = bench.build_line(measurements(source_hash="different"))
     assert line["roofline"]["traffic"] is None and line["roofline"]["ncu_artefact"]["matches_this_build"] is False
