@@ -47,7 +47,7 @@ struct Jac {
 
 // reference src/groups/mod.rs:228-247
 template <class F>
-BN_HD_NOINLINE Jac<F> jac_double(const Jac<F>& p) {
+BN_HD_NOINLINE Jac<F> jac_double(const Jac<F> p) {
     typedef typename F::T T;
     T a = F::sqr(p.x);
     T b = F::sqr(p.y);
@@ -70,7 +70,7 @@ BN_HD_NOINLINE Jac<F> jac_double(const Jac<F>& p) {
 
 // reference src/groups/mod.rs:272-312
 template <class F>
-BN_HD_NOINLINE Jac<F> jac_add(const Jac<F>& p, const Jac<F>& o) {
+BN_HD_NOINLINE Jac<F> jac_add(const Jac<F> p, const Jac<F> o) {
     typedef typename F::T T;
     if (F::is_zero(p.z)) return o;
     if (F::is_zero(o.z)) return p;

@@ -471,8 +471,15 @@ __global__ void __launch_bounds__(128) k_g2_eq(const uint32_t* __restrict__ a, c
 // set bits, about half) each perform one addition, and the owners read their result back.  Whole warps above c skip the
 // 16-multiplication addition instead of executing it with half of their lanes masked off (one thread per point with
 // per-lane branches costs 7 + 16 multiplications per step and warp; compacted, 7 + 16 * ceil(c / 32) / warps ~ 7 + 9).
-#define GMUL_THREADS_G1 256
+#ifndef GMUL_THREADS_G1
+#define GMUL_THREADS_G1 512   // run 14: 512 threads x 1 block 9.26 M/s; 256 x 2 8.97; 128 x 4 8.64; 256 x 1 (176 registers) 7.46; 768 x 1 (80 registers) 6.05
+#endif
+#ifndef GMUL_BLOCKS_G1
+#define GMUL_BLOCKS_G1 1
+#endif
+#ifndef GMUL_THREADS_G2
 #define GMUL_THREADS_G2 128
+#endif
 template <class F, int THREADS>
 __device__ __forceinline__ void g_mul_compact(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k, uint32_t* __restrict__ out,
                                               size_t n, uint32_t* smem) {
@@ -528,7 +535,7 @@ __device__ __forceinline__ void g_mul_compact(const uint32_t* __restrict__ p, co
 }
 extern __shared__ __align__(16) uint32_t gmul_smem[];
 #define GMUL_SMEM(F_WORDS, THREADS) ((size_t)(2 * (THREADS) * (F_WORDS) + (THREADS) + (THREADS) / 32) * 4)
-__global__ void __launch_bounds__(GMUL_THREADS_G1, 2) k_g1_mul_c(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k,
+__global__ void __launch_bounds__(GMUL_THREADS_G1, GMUL_BLOCKS_G1) k_g1_mul_c(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k,
                                                               uint32_t* __restrict__ out, size_t n) {
     g_mul_compact<FqOps, GMUL_THREADS_G1>(p, k, out, n, gmul_smem);
 }
