@@ -257,7 +257,7 @@ def build_roofline(m, clocks):
         "traffic": traffic,
         "bound_note": "integer modular arithmetic: neither HBM- nor tensor-bound (SURVEY.md section 8d); the denominator is the "
                       "IMAD.WIDE issue rate measured live by k_imad_peak: 8 lanes/clk/SMSP = 148*4*8*1.965e9 = 9.31e12/s, half of "
-                      "SURVEY.md's nominal 18.6e12 assumption (tools/ubench/pipes.cu times every 32x32 multiply form)",
+                      "SURVEY.md's nominal 18.6e12 assumption (tools/ubench/pipes2.cu times every 32x32 multiply form: none is cheaper per product bit)",
         "frac_of_survey_nominal_18.6T": achieved / 18.6e12,
         "algorithmic": "Fq mults of the reference algorithm x 136 IMAD: lines %d, Miller loop %d, final exponentiation %d (pairing: %d)"
                        % (M_LINES, M_MILLER, M_FEXP, M_PAIRING),

@@ -69,7 +69,7 @@ _inited = None
 def init(device: int = 0):
     """Bind this process to one CUDA device.  Raises if no device / not sm_100-class."""
     global _inited
-    if _inited != ("one", device):
+    if _inited != ("one", device) or load().bn_b200_device_count() == 0:
         check(load().bn_b200_init(int(device)))
         _inited = ("one", device)
     return load()
@@ -78,10 +78,17 @@ def init(device: int = 0):
 def init_multi(n_gpus: int = 0):
     """Bind devices 0..n_gpus-1 (0: all visible) to this process; host-pointer batches are then sharded over them."""
     global _inited
-    if _inited != ("multi", n_gpus):
+    if _inited != ("multi", n_gpus) or load().bn_b200_device_count() == 0:
         check(load().bn_b200_init_multi(int(n_gpus)))
         _inited = ("multi", n_gpus)
     return load()
+
+
+def shutdown():
+    """Release every bound device (streams, scratch, staging)."""
+    global _inited
+    check(load().bn_b200_shutdown())
+    _inited = None
 
 
 def ensure(device=None):
@@ -89,7 +96,7 @@ def ensure(device=None):
     bound (bn_b200.init / init_multi), binding device 0 if nothing is."""
     if device is not None:
         return init(device)
-    if _inited is None:
+    if _inited is None or load().bn_b200_device_count() == 0:
         return init(0)
     return load()
 

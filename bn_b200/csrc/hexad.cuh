@@ -618,19 +618,28 @@ BN_HD Fp2 hx_final_exp(const Ctx& c, const Fp2& f) {
     return hx_final_exp_with_inverse(c, f, hx_inv(c, f));
 }
 
-// Gt::pow, reference src/fields/mod.rs:35-46 via src/lib.rs:171: 256 squarings, generic (non-cyclotomic).
+// Gt::pow, reference src/fields/mod.rs:35-46 via src/lib.rs:171 (256 generic squarings, a multiplication per set bit).
+// Same value by fixed 2-bit windows: two squarings and at most one multiplication by a, a^2 or a^3 per window (the
+// product is computed by all hexads of the warp and selected per hexad; a zero window keeps the running value).  Valid for
+// ANY Fq12 element (no use of the cyclotomic structure); the result is canonical, hence the reference's bytes.
 // e = plain (de-Montgomerised) exponent, identical in all six lanes.
 template <class Ctx>
 BN_HD Fp2 hx_pow(const Ctx& c, const Fp2& a, const Fp& e) {
+    const Fp2 a2 = hx_sqr(c, a);
+    const Fp2 a3 = hx_mul(c, a2, a);
     Fp2 res = hx_one(c);
-    for (int i = 255; i >= 0; i--) {
-        res = hx_sqr(c, res);
+    for (int i = 127; i >= 0; i--) {
         uint32_t w = 0;
         BN_UNROLL
-        for (int l = 0; l < 8; l++) w = ((i >> 5) == l) ? e.v[l] : w;
-        bool bit = (w >> (i & 31)) & 1u;
-        Fp2 prod = hx_mul(c, a, res);  // computed by all hexads of the warp; selected per hexad
-        res = fp2_select(bit, prod, res);
+        for (int l = 0; l < 8; l++) w = ((i >> 4) == l) ? e.v[l] : w;
+        const uint32_t d = (w >> ((i & 15) * 2)) & 3u;
+        if (i != 127) {
+            res = hx_sqr(c, res);
+            res = hx_sqr(c, res);
+        }
+        const Fp2 m = fp2_select(d == 1, a, fp2_select(d == 2, a2, a3));
+        const Fp2 prod = hx_mul(c, res, m);
+        res = fp2_select(d != 0, prod, res);
     }
     return res;
 }

@@ -484,12 +484,12 @@ template <class F, int THREADS>
 __device__ __forceinline__ void g_mul_compact(const uint32_t* __restrict__ p, const uint32_t* __restrict__ k, uint32_t* __restrict__ out,
                                               size_t n, uint32_t* smem) {
     typedef JacIO<F> IO;
-    constexpr int WORDS = IO::WORDS, NW = THREADS / 32;
+    constexpr int WORDS = IO::WORDS;
     uint32_t* pbuf = smem;                                  // [THREADS][WORDS]: every thread's base point
     uint32_t* rbuf = smem + THREADS * WORDS;                // [THREADS][WORDS]: running points handed to the adders
     uint32_t* list = rbuf + THREADS * WORDS;                // [THREADS]: owners of the compacted additions
-    uint32_t* wcount = list + THREADS;                      // [NW]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* wcount = list + THREADS;                      // two slot counters (double-buffered by step parity)
+    const int tid = threadIdx.x, lane = tid & 31;
     const size_t i = (size_t)blockIdx.x * THREADS + tid;
     const bool active = i < n;
     const size_t ii = active ? i : n - 1;
@@ -500,29 +500,31 @@ __device__ __forceinline__ void g_mul_compact(const uint32_t* __restrict__ p, co
     res.y = F::one();
     res.z = F::zero();  // G::zero(), reference src/groups/mod.rs:208-214
     bool found_one = false;
+    if (tid < 2) wcount[tid] = 0;
+    __syncthreads();
+    int step = 0;
     for (int w = 7; w >= 0; w--) {
         uint32_t bits = 0;
 #pragma unroll
         for (int l = 0; l < 8; l++) bits = (w == l) ? sc.v[l] : bits;
-        for (int b = 31; b >= 0; b--) {
+        for (int b = 31; b >= 0; b--, step++) {
             if (found_one) res = jac_double<F>(res);
             const bool add = active && ((bits >> b) & 1u);
             const uint32_t m = __ballot_sync(0xffffffffu, add);
-            if (lane == 0) wcount[warp] = __popc(m);
-            __syncthreads();
-            int base = 0, total = 0;
-#pragma unroll
-            for (int x = 0; x < NW; x++) {
-                const int cx = (int)wcount[x];
-                base += x < warp ? cx : 0;
-                total += cx;
-            }
+            // slot allocation: one shared-memory atomic per warp on a double-buffered counter (the order of the compacted
+            // list is irrelevant), so a step needs two block barriers, not three
+            uint32_t* counter = wcount + (step & 1);
+            int base = 0;
+            if (lane == 0 && m) base = (int)atomicAdd(counter, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
             if (add) {
                 list[base + __popc(m & ((1u << lane) - 1u))] = tid;
                 IO::st(rbuf + tid * WORDS, res);
                 found_one = true;
             }
+            if (tid == 0) wcount[(step + 1) & 1] = 0;  // next step's counter (last read before the previous step's second barrier)
             __syncthreads();
+            const int total = (int)*counter;
             if (tid < total) {  // whole warps beyond `total` skip the addition
                 const int j = (int)list[tid];
                 IO::st(rbuf + j * WORDS, jac_add<F>(IO::ld_s(rbuf + j * WORDS), IO::ld_s(pbuf + j * WORDS)));
