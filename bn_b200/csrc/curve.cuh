@@ -45,56 +45,60 @@ struct Jac {
     typename F::T x, y, z;
 };
 
-// reference src/groups/mod.rs:228-247
+// Doubling.  The crate's G1 / G2 values are un-normalised Jacobian triples, so limb equality with the reference needs the
+// SAME sequence of canonical field operations as reference src/groups/mod.rs:228-247 (dbl-2009-l shape: X^2, Y^2, Y^4,
+// S = 2((X + Y^2)^2 - X^2 - Y^4), M = 3 X^2, X' = M^2 - 2S, Y' = M (S - X') - 8 Y^4, Z' = 2 Y Z); only the names are ours.
 template <class F>
 BN_HD_NOINLINE Jac<F> jac_double(const Jac<F> p) {
     typedef typename F::T T;
-    T a = F::sqr(p.x);
-    T b = F::sqr(p.y);
-    T c = F::sqr(b);
-    T d = F::sub(F::sub(F::sqr(F::add(p.x, b)), a), c);
-    d = F::add(d, d);
-    T e = F::add(F::add(a, a), a);
-    T f = F::sqr(e);
-    T x3 = F::sub(f, F::add(d, d));
-    T eight_c = F::add(c, c);
-    eight_c = F::add(eight_c, eight_c);
-    eight_c = F::add(eight_c, eight_c);
-    T y1z1 = F::mul(p.y, p.z);
+    const T xx = F::sqr(p.x);
+    const T yy = F::sqr(p.y);
+    const T yyyy = F::sqr(yy);
+    T s = F::sub(F::sub(F::sqr(F::add(p.x, yy)), xx), yyyy);
+    s = F::add(s, s);
+    const T m = F::add(F::add(xx, xx), xx);
+    const T mm = F::sqr(m);
+    const T xr = F::sub(mm, F::add(s, s));
+    T y4x8 = F::add(yyyy, yyyy);
+    y4x8 = F::add(y4x8, y4x8);
+    y4x8 = F::add(y4x8, y4x8);
+    const T yz = F::mul(p.y, p.z);
     Jac<F> r;
-    r.x = x3;
-    r.y = F::sub(F::mul(e, F::sub(d, x3)), eight_c);
-    r.z = F::add(y1z1, y1z1);
+    r.x = xr;
+    r.y = F::sub(F::mul(m, F::sub(s, xr)), y4x8);
+    r.z = F::add(yz, yz);
     return r;
 }
 
-// reference src/groups/mod.rs:272-312
+// Addition, same contract: the operation sequence of reference src/groups/mod.rs:272-312 (add-2007-bl shape), including
+// its early exits: an operand at infinity returns the other one, equal operands fall back to the doubling, and P + (-P)
+// runs through the general formula (giving a triple with z = 0 that is not the canonical (0, 1, 0)).
 template <class F>
 BN_HD_NOINLINE Jac<F> jac_add(const Jac<F> p, const Jac<F> o) {
     typedef typename F::T T;
     if (F::is_zero(p.z)) return o;
     if (F::is_zero(o.z)) return p;
-    T z1_squared = F::sqr(p.z);
-    T z2_squared = F::sqr(o.z);
-    T u1 = F::mul(p.x, z2_squared);
-    T u2 = F::mul(o.x, z1_squared);
-    T z1_cubed = F::mul(p.z, z1_squared);
-    T z2_cubed = F::mul(o.z, z2_squared);
-    T s1 = F::mul(p.y, z2_cubed);
-    T s2 = F::mul(o.y, z1_cubed);
-    if (F::eq(u1, u2) && F::eq(s1, s2)) return jac_double<F>(p);
-    T h = F::sub(u2, u1);
-    T s2_minus_s1 = F::sub(s2, s1);
-    T i = F::sqr(F::add(h, h));
-    T j = F::mul(h, i);
-    T r = F::add(s2_minus_s1, s2_minus_s1);
-    T v = F::mul(u1, i);
-    T s1_j = F::mul(s1, j);
-    T x3 = F::sub(F::sub(F::sqr(r), j), F::add(v, v));
+    const T zz1 = F::sqr(p.z);
+    const T zz2 = F::sqr(o.z);
+    const T ua = F::mul(p.x, zz2);
+    const T ub = F::mul(o.x, zz1);
+    const T zzz1 = F::mul(p.z, zz1);
+    const T zzz2 = F::mul(o.z, zz2);
+    const T sa = F::mul(p.y, zzz2);
+    const T sb = F::mul(o.y, zzz1);
+    if (F::eq(ua, ub) && F::eq(sa, sb)) return jac_double<F>(p);
+    const T dx = F::sub(ub, ua);
+    const T dy = F::sub(sb, sa);
+    const T fourdx2 = F::sqr(F::add(dx, dx));
+    const T cube = F::mul(dx, fourdx2);
+    const T slope2 = F::add(dy, dy);
+    const T base = F::mul(ua, fourdx2);
+    const T sac = F::mul(sa, cube);
+    const T xr = F::sub(F::sub(F::sqr(slope2), cube), F::add(base, base));
     Jac<F> out;
-    out.x = x3;
-    out.y = F::sub(F::mul(r, F::sub(v, x3)), F::add(s1_j, s1_j));
-    out.z = F::mul(F::sub(F::sub(F::sqr(F::add(p.z, o.z)), z1_squared), z2_squared), h);
+    out.x = xr;
+    out.y = F::sub(F::mul(slope2, F::sub(base, xr)), F::add(sac, sac));
+    out.z = F::mul(F::sub(F::sub(F::sqr(F::add(p.z, o.z)), zz1), zz2), dx);
     return out;
 }
 
