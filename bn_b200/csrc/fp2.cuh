@@ -240,6 +240,9 @@ BN_HD Fp lazy_reduce(Lazy9 x, const Row& row) {
     return r;
 }
 
+#ifndef BN_XI_IMAD
+#define BN_XI_IMAD 0
+#endif
 // multiply by xi = 9 + i:  (9x - y) + (9y + x) i.   reference src/fields/fq2.rs:70-72 (a full Fq2 mul there)
 template <class Row>
 BN_HD Fp2 fp2_mul_xi_tab(const Fp2& a, const Row& row) {
@@ -250,6 +253,23 @@ BN_HD Fp2 fp2_mul_xi_tab(const Fp2& a, const Row& row) {
         const Fp& x = comp == 0 ? a.c0 : a.c1;
         Fp addend = comp == 0 ? fp_neg_lazy<MQ>(a.c1) : a.c0;
         uint32_t v[9];
+#if BN_XI_IMAD
+        // v = addend + 9 x with the multiplier: two 4-instruction IMAD.WIDE chains on the (E, O) limb split of fp.cuh (the
+        // integer ALU is the busiest pipe of the hexad kernels, fmaheavy the idlest: 8 IMAD.WIDE + 11 ALU instructions
+        // instead of 27 ALU instructions)
+        uint32_t E[9], O[9];
+        BN_UNROLL
+        for (int i = 0; i < 8; i++) {
+            E[i] = addend.v[i];
+            O[i] = 0;
+        }
+        E[8] = 0;
+        O[8] = 0;
+        mad_row4(E, x.v[0], x.v[2], x.v[4], x.v[6], 9u);
+        mad_row4(O, x.v[1], x.v[3], x.v[5], x.v[7], 9u);
+        v[0] = E[0];
+        (void)add8(v + 1, E + 1, O);  // v[1..8] = E[1..8] + O[0..7]; O[8] = 0 (9 x_j < 2^36) and the total is below 2^288
+#else
         // v = x << 3
         v[0] = x.v[0] << 3;
         BN_UNROLL
@@ -259,6 +279,7 @@ BN_HD Fp2 fp2_mul_xi_tab(const Fp2& a, const Row& row) {
         v[8] += c;
         c = addi8(v, addend.v);
         v[8] += c;
+#endif
         fp_small_reduce9(v, comp == 0 ? r.c0.v : r.c1.v, row);
     }
     return r;

@@ -230,10 +230,11 @@ int bn_b200_set_max_chunk(size_t pairs);
 
 /* Per-kernel device timing of the most recent pairing_batch[_dev] call, measured with CUDA events on the
  * stream the kernels were launched on (enable first; reading synchronises that stream).
- * ms[0] = line-schedule kernel, ms[1] = Miller-loop + final-exponentiation kernels (two launches since run 28). */
+ * ms[0] = line-schedule kernel, ms[1] = Miller-loop, inversion and final-exponentiation kernels (three launches). */
 int bn_b200_set_profiling(int enable);
 int bn_b200_last_pairing_kernel_ms(float ms[2]);
-/* Same, three values: ms[0] = line schedule, ms[1] = Miller loop (k_miller), ms[2] = final exponentiation (k_fexp). */
+/* Same, three values: ms[0] = line schedule (k_pair_lines_duo), ms[1] = Miller loop incl. the preparation of the Fq12 inversion
+ * (k_miller), ms[2] = batch-wide Fq inversion + final exponentiation (k_fq_inv_batch + k_fexp). */
 int bn_b200_last_pairing_kernel_ms3(float ms[3]);
 /* Name of the i-th kernel of the pairing path (i = 0, 1, 2: the three values of bn_b200_last_pairing_kernel_ms3), NULL beyond. */
 const char* bn_b200_pairing_kernel_name(int i);
