@@ -92,4 +92,4 @@ def test_cpp_api_multi_gpu_one_process(exe, tmp_path):
     gt = body[m * 36:].reshape(m, 48)
     assert np.array_equal(gt, cref.pairing_batch(g1, g2, os.cpu_count() or 4))
     ratio = float(res.stdout.split("ratio ")[1].split()[0])
-    assert ratio > 0.8 * gpus, res.stdout   # the bar is 0.95 x (profiles/); the test guards against serialisation
+    assert ratio > 0.85 * gpus, res.stdout   # measured 0.96 x (2 GPUs) / 0.97 x (8 GPUs), profiles/; guards against serialisation
