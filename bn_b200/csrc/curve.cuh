@@ -10,7 +10,7 @@
 // HBM in the order the Miller kernel consumes them, already multiplied by P's coordinates and by xi where
 // a lane of the Miller kernel needs the wrapped coefficient.  (The reference keeps them in a heap Vec.)
 #pragma once
-#include "duo.cuh"
+#include "quad.cuh"
 #include "fp2.cuh"
 
 namespace bn {
@@ -171,7 +171,9 @@ struct Line {
 #define BN_NUM_LINES BN_NUM_LINES_BIN
 #endif
 
-// Fq2 multiplication policies for the line schedule: one thread per pairing, or a lane pair per pairing (duo.cuh).
+// Fq2 multiplication policies for the line schedule: one thread per pairing, a lane pair per pairing (duo.cuh), or
+// four lanes per pairing working on two operations at a time (quad.cuh; line_double / line_add have their own round
+// schedules for it below).
 struct SoloX {
     BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const { return fp2_mul(a, b); }
     BN_HD Fp2 sqr(const Fp2& a) const { return fp2_sqr(a); }
@@ -185,6 +187,22 @@ struct DuoX {
     BN_HD Fp2 sqr(const Fp2& a) const { return duo_sqr(d, a); }
     BN_HD Fp2 mul_fp(const Fp2& a, const Fp& k) const { return duo_mul_fp(d, a, k); }
     BN_HD Fp2 mul_xi(const Fp2& a) const { return duo_mul_xi(d, a); }
+};
+
+template <class Q>
+struct QuadX {  // whole-value wrappers over the four-lane rounds (to_affine only: both sides compute the same operation)
+    Q q;
+    BN_HD Fp own(const Fp2& a) const { return quad_own(q, a); }
+    BN_HD Fp2 whole(const Fp& m) const {
+        Fp o = q.partner(m);
+        return q.h() ? Fp2{o, m} : Fp2{m, o};
+    }
+    BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const {
+        return whole(quad_mul1(q, own(a), own(b)));
+    }
+    BN_HD Fp2 sqr(const Fp2& a) const {
+        return whole(quad_sqr1(q, own(a)));
+    }
 };
 
 template <class X>
@@ -233,6 +251,79 @@ BN_HD_NOINLINE Line line_add(const X& X_, G2Proj& r, const Fp2& bx, const Fp2& b
     r.z = X_.mul(r.z, h);
     Fp2 ell_0 = X_.mul_xi(fp2_sub(X_.mul(e, bx), X_.mul(d, by)));
     return make_line(X_, ell_0, d, fp2_neg(e), px, py);
+}
+
+// The same two steps as ROUNDS of two independent operations on four lanes (quad.cuh).  Values are OWN components
+// (component h of the Fq2 value); every value is computed by the same formula as above, so the lines and the running
+// point are bit-identical.
+struct G2ProjH {
+    Fp x, y, z;
+};
+// doubling (reference src/groups/mod.rs:612-634): 4 products + 6 squarings in 5 rounds
+template <class Q>
+BN_HD_NOINLINE LineH line_double_quad(const Q q, G2ProjH& r, Fp px, Fp py) {
+    Fp a, b, c, e, j, t, e_sq, g_sq;
+    quad_sqr2(q, r.y, r.z, b, c);
+    quad_sqr2(q, fp_add<MQ>(r.y, r.z), r.x, t, j);
+    quad_mul2(q, r.x, r.y, quad_own(q, g2_coeff_b()), fp_add<MQ>(fp_add<MQ>(c, c), c), a, e);
+    a = fp_half<MQ>(a);
+    Fp f = fp_add<MQ>(fp_add<MQ>(e, e), e);
+    Fp g = fp_half<MQ>(fp_add<MQ>(b, f));
+    Fp h = fp_sub<MQ>(t, fp_add<MQ>(b, c));
+    Fp i = fp_sub<MQ>(e, b);
+    quad_sqr2(q, e, g, e_sq, g_sq);
+    quad_mul2(q, a, fp_sub<MQ>(b, f), b, h, r.x, r.z);
+    r.y = fp_sub<MQ>(g_sq, fp_add<MQ>(fp_add<MQ>(e_sq, e_sq), e_sq));
+    return quad_finish_line(q, i, fp_neg<MQ>(h), fp_add<MQ>(fp_add<MQ>(j, j), j), px, py);
+}
+// addition (reference src/groups/mod.rs:592-610): 11 products + 2 squarings in 7 rounds (the last one holds one product)
+template <class Q>
+BN_HD_NOINLINE LineH line_add_quad(const Q q, G2ProjH& r, Fp bx, Fp by, Fp px, Fp py) {
+    Fp t0, t1, f, g, h, i, zg, ebx, dj, eij, hy;
+    quad_mul2(q, r.z, bx, r.z, by, t0, t1);
+    Fp d = fp_sub<MQ>(r.x, t0);
+    Fp e = fp_sub<MQ>(r.y, t1);
+    quad_sqr2(q, d, e, f, g);
+    quad_mul2(q, d, f, r.x, f, h, i);
+    quad_mul2(q, r.z, g, e, bx, zg, ebx);
+    Fp j = fp_sub<MQ>(fp_add<MQ>(zg, h), fp_add<MQ>(i, i));
+    quad_mul2(q, d, j, e, fp_sub<MQ>(i, j), dj, eij);
+    quad_mul2(q, h, r.y, r.z, h, hy, r.z);
+    r.x = dj;
+    r.y = fp_sub<MQ>(eij, hy);
+    return quad_finish_line(q, fp_sub<MQ>(ebx, quad_mul1(q, d, by)), d, fp_neg<MQ>(e), px, py);
+}
+// The line schedule of ate_lines below on four lanes.  sink(index, LineH).
+template <class Q, class Sink>
+BN_HD void ate_lines_quad(const Q& q, const Fp& px, const Fp& py, const Fp2& qx2, const Fp2& qy2, Sink& sink) {
+    const bool hi = q.h() != 0;
+    const Fp qx = quad_own(q, qx2), qy = quad_own(q, qy2);
+    G2ProjH r;
+    r.x = qx;
+    r.y = qy;
+    r.z = hi ? fp_zero() : fq_one();
+    int n = 0;
+#if BN_ATE_NAF
+    const Fp nqy = fp_neg<MQ>(qy);
+    for (int b = BN_ATE_NAF_DIGITS - 1; b >= 0; b--) {
+        sink(n++, line_double_quad(q, r, px, py));
+        if (b < 64 && ((BN_ATE_NAF_NZ >> b) & 1ULL))
+            sink(n++, line_add_quad(q, r, qx, ((BN_ATE_NAF_NEG >> b) & 1ULL) ? nqy : qy, px, py));
+    }
+#else
+    for (int b = BN_ATE_NBITS - 1; b >= 0; b--) {
+        sink(n++, line_double_quad(q, r, px, py));
+        if ((BN_ATE_BITS >> b) & 1ULL) sink(n++, line_add_quad(q, r, qx, qy, px, py));
+    }
+#endif
+    // twisted Frobenius (src/groups/mod.rs:550-555): conj = negate component 1
+    const Fp gx = quad_own(q, FROB_GAMMA_C[0][2]), gy = quad_own(q, FROB_GAMMA_C[0][3]);
+    Fp q1x, q1y, q2x, q2y;
+    quad_mul2(q, gx, hi ? fp_neg<MQ>(qx) : qx, gy, hi ? fp_neg<MQ>(qy) : qy, q1x, q1y);
+    quad_mul2(q, gx, hi ? fp_neg<MQ>(q1x) : q1x, gy, hi ? fp_neg<MQ>(q1y) : q1y, q2x, q2y);
+    q2y = fp_neg<MQ>(q2y);
+    sink(n++, line_add_quad(q, r, q1x, q1y, px, py));
+    sink(n++, line_add_quad(q, r, q2x, q2y, px, py));
 }
 
 // twisted Frobenius: reference src/groups/mod.rs:550-555

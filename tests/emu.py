@@ -89,6 +89,14 @@ def lines_duo(g1, g2, variant="product"):
     return finite, o0, o1
 
 
+def lines_quad(g1, g2, variant="product", lanes=4):
+    g1, g2 = _c(g1), _c(g2)
+    L = lib(variant)
+    out = np.zeros((L.emu_num_lines(), 40), dtype=np.uint64)
+    finite = (L.emu_lines_quad if lanes == 4 else L.emu_lines_pair)(_p(g1), _p(g2), _p(out))
+    return finite, out
+
+
 def gt_op(op, a, b=None, arg=0):
     a, b = _c(a), _c(b)
     out = np.zeros(48, dtype=np.uint64)

@@ -128,6 +128,21 @@ def test_duo_line_schedule_equals_solo(pairs):
             assert np.array_equal(L, L0) and np.array_equal(L, L1)
 
 
+@pytest.mark.parametrize("lanes", [4, 2])
+@pytest.mark.parametrize("variant", ["product", "refchain"])
+def test_quad_line_schedule_equals_solo(pairs, variant, lanes):
+    """quad.cuh: the four-lane line kernel (two operations per round, one Fq2 component per lane) stores the same lines
+    as the one-thread version, for the NAF schedule and for the reference's binary chain (src/groups/mod.rs:557-588)."""
+    g1, g2, _ = pairs
+    e1, e2 = util.edge_case_pairs()
+    for a, b in [(g1[0], g2[0]), (g1[1], g2[1]), (g1[2], g2[3]), (e1[0], e2[0]), (e1[6], e2[6]), (e1[1], e2[1])]:
+        finite, L, _, _ = emu.lines(a, b, variant)
+        f2, Lq = emu.lines_quad(a, b, variant, lanes)
+        assert finite == f2
+        if finite:
+            assert np.array_equal(L, Lq)
+
+
 def test_hexad_fq12_ops(pairs):
     _, _, gt = pairs
     a, b = gt[0], gt[1]
