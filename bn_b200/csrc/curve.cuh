@@ -10,7 +10,7 @@
 // HBM in the order the Miller kernel consumes them, already multiplied by P's coordinates and by xi where
 // a lane of the Miller kernel needs the wrapped coefficient.  (The reference keeps them in a heap Vec.)
 #pragma once
-#include "quad.cuh"
+#include "duo.cuh"
 #include "fp2.cuh"
 
 namespace bn {
@@ -171,9 +171,8 @@ struct Line {
 #define BN_NUM_LINES BN_NUM_LINES_BIN
 #endif
 
-// Fq2 multiplication policies for the line schedule: one thread per pairing, a lane pair per pairing (duo.cuh), or
-// four lanes per pairing working on two operations at a time (quad.cuh; line_double / line_add have their own round
-// schedules for it below).
+// Fq2 multiplication policies for to_affine and the one-thread line schedule; the lane-pair schedule (duo.cuh) has its
+// own step functions below (line_double_duo, line_add_duo) and uses DuoX for to_affine only.
 struct SoloX {
     BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const { return fp2_mul(a, b); }
     BN_HD Fp2 sqr(const Fp2& a) const { return fp2_sqr(a); }
@@ -181,28 +180,10 @@ struct SoloX {
     BN_HD Fp2 mul_xi(const Fp2& a) const { return fp2_mul_xi(a); }
 };
 template <class D>
-struct DuoX {
+struct DuoX {  // whole Fq2 values in, whole values out (both lanes), computed by the pair
     D d;
-    BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const { return duo_mul(d, a, b); }
-    BN_HD Fp2 sqr(const Fp2& a) const { return duo_sqr(d, a); }
-    BN_HD Fp2 mul_fp(const Fp2& a, const Fp& k) const { return duo_mul_fp(d, a, k); }
-    BN_HD Fp2 mul_xi(const Fp2& a) const { return duo_mul_xi(d, a); }
-};
-
-template <class Q>
-struct QuadX {  // whole-value wrappers over the four-lane rounds (to_affine only: both sides compute the same operation)
-    Q q;
-    BN_HD Fp own(const Fp2& a) const { return quad_own(q, a); }
-    BN_HD Fp2 whole(const Fp& m) const {
-        Fp o = q.partner(m);
-        return q.h() ? Fp2{o, m} : Fp2{m, o};
-    }
-    BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const {
-        return whole(quad_mul1(q, own(a), own(b)));
-    }
-    BN_HD Fp2 sqr(const Fp2& a) const {
-        return whole(quad_sqr1(q, own(a)));
-    }
+    BN_HD Fp2 mul(const Fp2& a, const Fp2& b) const { return duo_whole(d, duo_mul(d, duo_own(d, a), duo_own(d, b))); }
+    BN_HD Fp2 sqr(const Fp2& a) const { return duo_whole(d, duo_sqr(d, duo_own(d, a))); }
 };
 
 template <class X>
@@ -253,51 +234,65 @@ BN_HD_NOINLINE Line line_add(const X& X_, G2Proj& r, const Fp2& bx, const Fp2& b
     return make_line(X_, ell_0, d, fp2_neg(e), px, py);
 }
 
-// The same two steps as ROUNDS of two independent operations on four lanes (quad.cuh).  Values are OWN components
-// (component h of the Fq2 value); every value is computed by the same formula as above, so the lines and the running
-// point are bit-identical.
+// The same two steps on a lane pair (duo.cuh).  Every value is the lane's OWN component (component h) of the Fq2 value
+// of the same name above and is computed by the same formula, so lines and running point are bit-identical.
 struct G2ProjH {
     Fp x, y, z;
 };
-// doubling (reference src/groups/mod.rs:612-634): 4 products + 6 squarings in 5 rounds
-template <class Q>
-BN_HD_NOINLINE LineH line_double_quad(const Q q, G2ProjH& r, Fp px, Fp py) {
-    Fp a, b, c, e, j, t, e_sq, g_sq;
-    quad_sqr2(q, r.y, r.z, b, c);
-    quad_sqr2(q, fp_add<MQ>(r.y, r.z), r.x, t, j);
-    quad_mul2(q, r.x, r.y, quad_own(q, g2_coeff_b()), fp_add<MQ>(fp_add<MQ>(c, c), c), a, e);
-    a = fp_half<MQ>(a);
+struct LineH {
+    Fp l0, l3, xl3, l4, xl4;
+};
+template <class D>
+BN_HD LineH make_line_duo(const D& d, const Fp& ell_0_pre, const Fp& ell_vw, const Fp& ell_vv, const Fp& px, const Fp& py) {
+    LineH L;
+    L.l3 = duo_mul_fp(ell_vw, py);
+    L.l4 = duo_mul_fp(ell_vv, px);
+    L.xl3 = duo_mul_xi(d, L.l3);
+    L.xl4 = duo_mul_xi(d, L.l4);
+    L.l0 = duo_mul_xi(d, ell_0_pre);
+    return L;
+}
+// reference src/groups/mod.rs:612-634
+template <class D>
+BN_HD_NOINLINE LineH line_double_duo(const D d, G2ProjH& r, Fp px, Fp py) {
+    Fp b = duo_sqr(d, r.y);
+    Fp c = duo_sqr(d, r.z);
+    Fp t = duo_sqr(d, fp_add<MQ>(r.y, r.z));
+    Fp j = duo_sqr(d, r.x);
+    Fp a = fp_half<MQ>(duo_mul(d, r.x, r.y));
+    Fp e = duo_mul(d, duo_own(d, g2_coeff_b()), fp_add<MQ>(fp_add<MQ>(c, c), c));
     Fp f = fp_add<MQ>(fp_add<MQ>(e, e), e);
     Fp g = fp_half<MQ>(fp_add<MQ>(b, f));
     Fp h = fp_sub<MQ>(t, fp_add<MQ>(b, c));
     Fp i = fp_sub<MQ>(e, b);
-    quad_sqr2(q, e, g, e_sq, g_sq);
-    quad_mul2(q, a, fp_sub<MQ>(b, f), b, h, r.x, r.z);
+    Fp e_sq = duo_sqr(d, e);
+    Fp g_sq = duo_sqr(d, g);
+    r.x = duo_mul(d, a, fp_sub<MQ>(b, f));
+    r.z = duo_mul(d, b, h);
     r.y = fp_sub<MQ>(g_sq, fp_add<MQ>(fp_add<MQ>(e_sq, e_sq), e_sq));
-    return quad_finish_line(q, i, fp_neg<MQ>(h), fp_add<MQ>(fp_add<MQ>(j, j), j), px, py);
+    return make_line_duo(d, i, fp_neg<MQ>(h), fp_add<MQ>(fp_add<MQ>(j, j), j), px, py);
 }
-// addition (reference src/groups/mod.rs:592-610): 11 products + 2 squarings in 7 rounds (the last one holds one product)
-template <class Q>
-BN_HD_NOINLINE LineH line_add_quad(const Q q, G2ProjH& r, Fp bx, Fp by, Fp px, Fp py) {
-    Fp t0, t1, f, g, h, i, zg, ebx, dj, eij, hy;
-    quad_mul2(q, r.z, bx, r.z, by, t0, t1);
-    Fp d = fp_sub<MQ>(r.x, t0);
-    Fp e = fp_sub<MQ>(r.y, t1);
-    quad_sqr2(q, d, e, f, g);
-    quad_mul2(q, d, f, r.x, f, h, i);
-    quad_mul2(q, r.z, g, e, bx, zg, ebx);
-    Fp j = fp_sub<MQ>(fp_add<MQ>(zg, h), fp_add<MQ>(i, i));
-    quad_mul2(q, d, j, e, fp_sub<MQ>(i, j), dj, eij);
-    quad_mul2(q, h, r.y, r.z, h, hy, r.z);
-    r.x = dj;
-    r.y = fp_sub<MQ>(eij, hy);
-    return quad_finish_line(q, fp_sub<MQ>(ebx, quad_mul1(q, d, by)), d, fp_neg<MQ>(e), px, py);
+// reference src/groups/mod.rs:592-610
+template <class D>
+BN_HD_NOINLINE LineH line_add_duo(const D d, G2ProjH& r, Fp bx, Fp by, Fp px, Fp py) {
+    Fp dd = fp_sub<MQ>(r.x, duo_mul(d, r.z, bx));
+    Fp e = fp_sub<MQ>(r.y, duo_mul(d, r.z, by));
+    Fp f = duo_sqr(d, dd);
+    Fp g = duo_sqr(d, e);
+    Fp h = duo_mul(d, dd, f);
+    Fp i = duo_mul(d, r.x, f);
+    Fp j = fp_sub<MQ>(fp_add<MQ>(duo_mul(d, r.z, g), h), fp_add<MQ>(i, i));
+    r.x = duo_mul(d, dd, j);
+    r.y = fp_sub<MQ>(duo_mul(d, e, fp_sub<MQ>(i, j)), duo_mul(d, h, r.y));
+    r.z = duo_mul(d, r.z, h);
+    Fp ell_0_pre = fp_sub<MQ>(duo_mul(d, e, bx), duo_mul(d, dd, by));
+    return make_line_duo(d, ell_0_pre, dd, fp_neg<MQ>(e), px, py);
 }
-// The line schedule of ate_lines below on four lanes.  sink(index, LineH).
-template <class Q, class Sink>
-BN_HD void ate_lines_quad(const Q& q, const Fp& px, const Fp& py, const Fp2& qx2, const Fp2& qy2, Sink& sink) {
-    const bool hi = q.h() != 0;
-    const Fp qx = quad_own(q, qx2), qy = quad_own(q, qy2);
+// ate_lines (below) on a lane pair.  sink(index, LineH).
+template <class D, class Sink>
+BN_HD void ate_lines_duo(const D& d, const Fp& px, const Fp& py, const Fp2& qx2, const Fp2& qy2, Sink& sink) {
+    const bool hi = d.h() != 0;
+    const Fp qx = duo_own(d, qx2), qy = duo_own(d, qy2);
     G2ProjH r;
     r.x = qx;
     r.y = qy;
@@ -306,24 +301,22 @@ BN_HD void ate_lines_quad(const Q& q, const Fp& px, const Fp& py, const Fp2& qx2
 #if BN_ATE_NAF
     const Fp nqy = fp_neg<MQ>(qy);
     for (int b = BN_ATE_NAF_DIGITS - 1; b >= 0; b--) {
-        sink(n++, line_double_quad(q, r, px, py));
+        sink(n++, line_double_duo(d, r, px, py));
         if (b < 64 && ((BN_ATE_NAF_NZ >> b) & 1ULL))
-            sink(n++, line_add_quad(q, r, qx, ((BN_ATE_NAF_NEG >> b) & 1ULL) ? nqy : qy, px, py));
+            sink(n++, line_add_duo(d, r, qx, ((BN_ATE_NAF_NEG >> b) & 1ULL) ? nqy : qy, px, py));
     }
 #else
     for (int b = BN_ATE_NBITS - 1; b >= 0; b--) {
-        sink(n++, line_double_quad(q, r, px, py));
-        if ((BN_ATE_BITS >> b) & 1ULL) sink(n++, line_add_quad(q, r, qx, qy, px, py));
+        sink(n++, line_double_duo(d, r, px, py));
+        if ((BN_ATE_BITS >> b) & 1ULL) sink(n++, line_add_duo(d, r, qx, qy, px, py));
     }
 #endif
-    // twisted Frobenius (src/groups/mod.rs:550-555): conj = negate component 1
-    const Fp gx = quad_own(q, FROB_GAMMA_C[0][2]), gy = quad_own(q, FROB_GAMMA_C[0][3]);
-    Fp q1x, q1y, q2x, q2y;
-    quad_mul2(q, gx, hi ? fp_neg<MQ>(qx) : qx, gy, hi ? fp_neg<MQ>(qy) : qy, q1x, q1y);
-    quad_mul2(q, gx, hi ? fp_neg<MQ>(q1x) : q1x, gy, hi ? fp_neg<MQ>(q1y) : q1y, q2x, q2y);
-    q2y = fp_neg<MQ>(q2y);
-    sink(n++, line_add_quad(q, r, q1x, q1y, px, py));
-    sink(n++, line_add_quad(q, r, q2x, q2y, px, py));
+    // twisted Frobenius (src/groups/mod.rs:550-555); conj negates component 1
+    const Fp gx = duo_own(d, FROB_GAMMA_C[0][2]), gy = duo_own(d, FROB_GAMMA_C[0][3]);
+    Fp q1x = duo_mul(d, gx, hi ? fp_neg<MQ>(qx) : qx), q1y = duo_mul(d, gy, hi ? fp_neg<MQ>(qy) : qy);
+    Fp q2x = duo_mul(d, gx, hi ? fp_neg<MQ>(q1x) : q1x), q2y = fp_neg<MQ>(duo_mul(d, gy, hi ? fp_neg<MQ>(q1y) : q1y));
+    sink(n++, line_add_duo(d, r, q1x, q1y, px, py));
+    sink(n++, line_add_duo(d, r, q2x, q2y, px, py));
 }
 
 // twisted Frobenius: reference src/groups/mod.rs:550-555

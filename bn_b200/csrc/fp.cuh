@@ -29,6 +29,10 @@
 #define BN_HD_NOINLINE inline
 #endif
 
+#ifndef BN_MUL_FUSED
+#define BN_MUL_FUSED 1   // fp_mul / fp_mul2: product and reduction rows interleaved on one accumulator (0: product, merge, reduce)
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define BN_UNROLL _Pragma("unroll")
 #else
@@ -829,12 +833,68 @@ BN_HD Fp mont_reduce(const Wide& T) {
     return r;
 }
 
+// Product and Montgomery reduction interleaved row by row (coarsely integrated operand scanning, the order of reference
+// src/arith.rs:257-263 / mul_reduce) on ONE (E, O) pair: row i adds a*b_i (and c*d_i when TWO), then m_i*p with
+// m_i = -(limb i)/p mod 2^32, which cancels limb i.  Every chain's carry lands in the window's top limb, which no earlier
+// row has multiplied into (as in wide_mac2), so the 512-bit product is never merged: against wide_mac + mont_reduce_raw
+// this saves the 16-limb merge of the product and the final addition of its high half (24 IADD3 of ~200 instructions).
+// Returns (a*b [+ c*d] + m*p) / 2^256 in [0, (a*b [+ c*d]) / 2^256 + p): the same integer mont_reduce_raw returns.
+template <class M, bool TWO>
+BN_HD void mul_reduce_rows(uint32_t* r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+    uint32_t E[18], O[16];
+    BN_UNROLL
+    for (int i = 0; i < 18; i++) E[i] = 0;
+    BN_UNROLL
+    for (int i = 0; i < 16; i++) O[i] = 0;
+    const uint32_t q0 = M::m(0), q1 = M::m(1), q2 = M::m(2), q3 = M::m(3), q4 = M::m(4), q5 = M::m(5),
+                   q6 = M::m(6), q7 = M::m(7);
+    BN_UNROLL
+    for (int i = 0; i < 8; i++) {
+        eo_row(E, O, a.v, b.v[i], i);
+        if (TWO) eo_row(E, O, c.v, d.v[i], i);
+        uint32_t low = (i == 0) ? E[0] : (E[i] + O[i - 1]);
+        uint32_t mi = low * M::inv();
+        if ((i & 1) == 0) {
+            mad_row4(&E[i], q0, q2, q4, q6, mi);
+            if (i == 0)
+                mad_row4(&O[0], q1, q3, q5, q7, mi);
+            else
+                mad_row4_fold(&O[i], q1, q3, q5, q7, mi, E[i], O[i - 1], true);
+        } else {
+            mad_row4(&O[i - 1], q0, q2, q4, q6, mi);
+            mad_row4_fold(&E[i + 1], q1, q3, q5, q7, mi, E[i], O[i - 1], true);
+        }
+    }
+    (void)add8(r, &E[8], &O[7]);
+}
 // a*b*R^-1 mod p, canonical.   reference src/arith.rs:257-263 (mul_reduce + final correction)
 template <class M>
 BN_HD Fp fp_mul(const Fp& a, const Fp& b) {
+#if BN_MUL_FUSED
+    Fp r;
+    mul_reduce_rows<M, false>(r.v, a, b, a, b);
+    cond_sub_p<M>(r.v);
+    return r;
+#else
     Wide T = wide_zero();
     wide_mac1(T, a, b);
     return mont_reduce<M, 2>(T);
+#endif
+}
+// (a*b + c*d)*R^-1 mod p, canonical, for a*b + c*d < 2^256 p (e.g. all four < p, or one factor of each product <= p and
+// the other < 2p... see the callers)
+template <class M>
+BN_HD Fp fp_mul2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#if BN_MUL_FUSED
+    Fp r;
+    mul_reduce_rows<M, true>(r.v, a, b, c, d);
+    cond_sub_p<M>(r.v);
+    return r;
+#else
+    Wide T = wide_zero();
+    wide_mac2(T, a, b, c, d);
+    return mont_reduce<M, 2>(T);
+#endif
 }
 // out-of-line copy for the thread-per-element kernels (keeps their code inside the instruction cache)
 template <class M>

@@ -136,20 +136,15 @@ BN_HD Fp fp_neg_2q(const Fp& a) {
 // reference src/fields/fq2.rs:139-155 (Karatsuba + 3-4 reductions there; same canonical result).
 BN_HD_NOINLINE Fp2 fp2_mul(Fp2 a, Fp2 b) {
     Fp nb1 = fp_neg_lazy<MQ>(b.c1);
-    Wide t0 = wide_zero(), t1 = wide_zero();
-    wide_mac2(t0, a.c0, b.c0, a.c1, nb1);   // a0 b0 - a1 b1   (< 2 q^2)
-    wide_mac2(t1, a.c0, b.c1, a.c1, b.c0);  // a0 b1 + a1 b0
-    return Fp2{mont_reduce<MQ, 2>(t0), mont_reduce<MQ, 2>(t1)};
+    return Fp2{fp_mul2<MQ>(a.c0, b.c0, a.c1, nb1),    // a0 b0 - a1 b1   (< 2 q^2)
+               fp_mul2<MQ>(a.c0, b.c1, a.c1, b.c0)};  // a0 b1 + a1 b0
 }
 // (a0+a1)(a0-a1) + 2 a0 a1 i.   reference src/fields/fq2.rs:112-123
 BN_HD_NOINLINE Fp2 fp2_sqr(Fp2 a) {
     Fp s = fp_add_raw(a.c0, a.c1);                      // < 2q
     Fp d = fp_add_raw(a.c0, fp_neg_lazy<MQ>(a.c1));     // a0 + (q - a1) in (0, 2q)
-    Wide t0 = wide_zero(), t1 = wide_zero();
-    wide_mac1(t0, s, d);  // < 4 q^2 -> raw < 1.76 q
-    wide_mac1(t1, a.c0, a.c1);
-    wide_dbl(t1);
-    return Fp2{mont_reduce<MQ, 2>(t0), mont_reduce<MQ, 2>(t1)};
+    // s d < 4 q^2 -> raw < 1.76 q; (2 a0) a1 < 2 q^2
+    return Fp2{fp_mul<MQ>(s, d), fp_mul<MQ>(fp_add_raw(a.c0, a.c0), a.c1)};
 }
 // scale by an Fq element.   reference src/fields/fq2.rs:63-68
 BN_HD Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return Fp2{fp_mul<MQ>(a.c0, k), fp_mul<MQ>(a.c1, k)}; }

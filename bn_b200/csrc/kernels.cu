@@ -4,9 +4,9 @@
 //   k_fq_mul_chain    K1  Fq Montgomery multiply chain (BASELINE config 2); k_imad_peak calibrates the IMAD.WIDE roofline
 //   k_g1_mul/k_g2_mul K3  batched scalar multiplication, one thread per point (reference's chain: Jacobian limbs match)
 //   k_pair_lines_duo  K4a to_affine (one inversion per pair, batched per block) + the ate line schedule (88 lines, NAF
-//                         walk of 6u+2), one LANE PAIR per pairing, streamed to HBM in consumption order
-//                         (k_pair_lines_quad: four lanes per pairing, two operations per round, quad.cuh; k_pair_lines_duo:
-//                         lane pair per pairing; k_pair_lines: one thread per pairing; A/B via BN_B200_LINES=quad|duo|solo)
+//                         walk of 6u+2), one LANE PAIR per pairing (one Fq2 component per lane, duo.cuh), streamed to HBM
+//                         in consumption order
+//                         (k_pair_lines: the one-thread-per-pairing form, kept for A/B via BN_B200_LINES=solo)
 //   k_miller          K4b Miller accumulation, one 6-lane hexad per pairing (5 per warp, 3 blocks/SM); Fq12 state in
 //                         registers, operands exchanged through shared-memory slots (LDS/STS by 32-bit shared address),
 //                         line coefficients read from a TMA-fed ring; writes the unreduced Miller value to the output
@@ -733,83 +733,15 @@ __global__ void __launch_bounds__(64) k_pair_lines(const uint32_t* __restrict__ 
     ate_lines(X_, px, py, qx, qy, sink);
 }
 
-// K4a, lane-pair form (duo.cuh): lanes (2j, 2j+1) compute the lines of one pairing, one Fq2 output component each.
+// K4a, lane-pair form (duo.cuh): lanes (2j, 2j+1) hold component 0 / 1 of every Fq2 value of pairing j.
+// A pair's exchange area: 2 x 64 B (two operands per lane) + 16 B of padding that puts adjacent pairs on different banks.
+// Every exchange is __syncwarp | write | __syncwarp | read: the first barrier says the partner has read the previous one.
+#define DUO_XCH_WORDS 36
 struct DevDuo {
     int hh;
-    uint32_t kq;  // shared address of the k*q table
-    __device__ __forceinline__ int h() const { return hh; }
-    __device__ __forceinline__ void small_reduce9(uint32_t* v, uint32_t* out) const { fp_small_reduce9(v, out, KqRowLds{kq}); }
-    __device__ __forceinline__ Fp swap(const Fp& v) const {
-        Fp r;
-#pragma unroll
-        for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, v.v[i], 1);
-        return r;
-    }
-};
-struct DevDuoLineSink {
-    uint32_t* base;
-    size_t n, pidx;
-    int h;
-    bool active;
-    // both lanes hold the whole line; lane 0 stores words [0,40), lane 1 stores [40,80)
-    __device__ __forceinline__ void operator()(int t, const Line& L) const {
-        if (!active) return;
-        uint32_t* p = base + ((size_t)t * n + pidx) * BN_LINE_WORDS;
-        if (h == 0) {
-            st_fp2(p + BN_LINE_OFF_L0, L.l0);
-            st_fp2(p + BN_LINE_OFF_L3, L.l3);
-            st_fp(p + BN_LINE_OFF_XL3, L.xl3.c0);
-        } else {
-            st_fp(p + BN_LINE_OFF_XL3 + 8, L.xl3.c1);
-            st_fp2(p + BN_LINE_OFF_L4, L.l4);
-            st_fp2(p + BN_LINE_OFF_XL4, L.xl4);
-        }
-    }
-};
-#ifndef DUO_BLOCK
-#define DUO_BLOCK 32   // threads per block (run 23: 32 -> 1.589 ms, 64 -> 1.613 ms, 128 -> 1.614 ms); of the lane-pair line kernel (DUO_BLOCK/2 pairings share one batched inversion)
-#endif
-__global__ void __launch_bounds__(DUO_BLOCK) k_pair_lines_duo(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
-                                                       uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t i = t >> 1;
-    const bool active = i < n;
-    if (!active) i = n - 1;  // keep whole warps alive for the shuffles
-    Jac<FqOps> P;
-    P.x = ld_fp(g1 + i * 24);
-    P.y = ld_fp(g1 + i * 24 + 8);
-    P.z = ld_fp(g1 + i * 24 + 16);
-    Jac<Fq2Ops> Q;
-    Q.x = ld_fp2(g2 + i * 48);
-    Q.y = ld_fp2(g2 + i * 48 + 16);
-    Q.z = ld_fp2(g2 + i * 48 + 32);
-    __shared__ alignas(16) uint32_t s_kq[16 * BN_KQ_STRIDE];  // k*q rows for the xi-multiplication's reduction
-    if (threadIdx.x < 16) kq_table_fill(s_kq, threadIdx.x);
-    __syncthreads();
-    DuoX<DevDuo> X_{DevDuo{(int)(t & 1), smem_u32(s_kq)}};
-    Fp px, py;
-    Fp2 qx, qy;
-    __shared__ Fp s_val[DUO_BLOCK / 2], s_pre[DUO_BLOCK / 2];  // one slot per pairing of the block
-    const int slot = (int)(threadIdx.x >> 1);
-    auto inv = [&](const Fp& x) { return block_batch_inv(x, (threadIdx.x & 1) == 0 ? slot : -1, slot, DUO_BLOCK / 2, s_val, s_pre); };
-    bool finite = pair_to_affine(X_, inv, P, Q, px, py, qx, qy);
-    if (active && (t & 1) == 0) flags[i] = finite ? 1 : 0;
-    DevDuoLineSink sink{lines, n, i, (int)(t & 1), active};
-    ate_lines(X_, px, py, qx, qy, sink);
-}
-
-// K4a, four-lane form (quad.cuh): lanes 4j .. 4j+3 compute the lines of pairing j, two Fq2 operations per round, one
-// component per lane.  A quad's exchange area: pre[4][2] (operands for the partner, 64 B per lane) | post[4] (results
-// for the other side, 32 B per lane) | 16 B of padding that puts adjacent quads on different banks.  Every exchange is
-// __syncwarp | write | __syncwarp | read: the first barrier says that all lanes have read the area's previous contents.
-#define QUAD_XCH_WORDS 100
-struct DevQuad {
-    static constexpr int SIDES = 2;
-    int hh, ss;
     uint32_t kq;   // shared address of the k*q table
-    uint32_t xch;  // shared address of this quad's exchange area
+    uint32_t xch;  // shared address of this pair's exchange area
     __device__ __forceinline__ int h() const { return hh; }
-    __device__ __forceinline__ int s() const { return ss; }
     __device__ __forceinline__ void small_reduce9(uint32_t* v, uint32_t* out) const { fp_small_reduce9(v, out, KqRowLds{kq}); }
     __device__ __forceinline__ static void put(uint32_t addr, const Fp& v) {
         sts128(addr, v.v);
@@ -822,7 +754,7 @@ struct DevQuad {
         return r;
     }
     __device__ __forceinline__ void partner2(const Fp& a, const Fp& b, Fp& ao, Fp& bo) const {
-        const uint32_t me = xch + (uint32_t)(2 * ss + hh) * 64, other = xch + (uint32_t)(2 * ss + (hh ^ 1)) * 64;
+        const uint32_t me = xch + (uint32_t)hh * 64, other = xch + (uint32_t)(hh ^ 1) * 64;
         __syncwarp();
         put(me, a);
         put(me + 32, b);
@@ -832,95 +764,12 @@ struct DevQuad {
     }
     __device__ __forceinline__ Fp partner(const Fp& a) const {
         __syncwarp();
-        put(xch + (uint32_t)(2 * ss + hh) * 64, a);
+        put(xch + (uint32_t)hh * 64, a);
         __syncwarp();
-        return get(xch + (uint32_t)(2 * ss + (hh ^ 1)) * 64);
-    }
-    __device__ __forceinline__ void sides(const Fp& mine, Fp& rA, Fp& rB) const {
-        const uint32_t post = xch + 256;
-        __syncwarp();
-        put(post + (uint32_t)(2 * ss + hh) * 32, mine);
-        __syncwarp();
-        rA = get(post + (uint32_t)hh * 32);
-        rB = get(post + (uint32_t)(2 + hh) * 32);
+        return get(xch + (uint32_t)(hh ^ 1) * 64);
     }
 };
-struct DevQuadLineSink {
-    uint32_t* base;
-    size_t n, pidx;
-    int h, s;
-    bool active;
-    // lane (s, h) stores component h of l0 (side 0 only), of l3 / xl3 (side 0) or of l4 / xl4 (side 1)
-    __device__ __forceinline__ void operator()(int t, const LineH& L) const {
-        if (!active) return;
-        uint32_t* p = base + ((size_t)t * n + pidx) * BN_LINE_WORDS + 8 * h;
-        if (s == 0) st_fp(p + BN_LINE_OFF_L0, L.l0);
-        st_fp(p + (s ? BN_LINE_OFF_L4 : BN_LINE_OFF_L3), L.l3);   // side 1: l3 == l4, xl3 == xl4 (quad_finish_line)
-        st_fp(p + (s ? BN_LINE_OFF_XL4 : BN_LINE_OFF_XL3), L.xl3);
-    }
-};
-#ifndef QUAD_BLOCK
-#define QUAD_BLOCK 32   // threads per block: QUAD_BLOCK/4 pairings share one batched inversion
-#endif
-__global__ void __launch_bounds__(QUAD_BLOCK) k_pair_lines_quad(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
-                                                         uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t i = t >> 2;
-    const bool active = i < n;
-    if (!active) i = n - 1;  // keep whole warps alive for the exchanges
-    Jac<FqOps> P;
-    P.x = ld_fp(g1 + i * 24);
-    P.y = ld_fp(g1 + i * 24 + 8);
-    P.z = ld_fp(g1 + i * 24 + 16);
-    Jac<Fq2Ops> Q;
-    Q.x = ld_fp2(g2 + i * 48);
-    Q.y = ld_fp2(g2 + i * 48 + 16);
-    Q.z = ld_fp2(g2 + i * 48 + 32);
-    __shared__ alignas(16) uint32_t s_kq[16 * BN_KQ_STRIDE];
-    __shared__ alignas(16) uint32_t s_xch[(QUAD_BLOCK / 4) * QUAD_XCH_WORDS];
-    if (threadIdx.x < 16) kq_table_fill(s_kq, threadIdx.x);
-    __syncthreads();
-    const int slot = (int)(threadIdx.x >> 2);
-    const int l4 = (int)(threadIdx.x & 3);
-    QuadX<DevQuad> X_{DevQuad{l4 & 1, l4 >> 1, smem_u32(s_kq), smem_u32(s_xch + slot * QUAD_XCH_WORDS)}};
-    Fp px, py;
-    Fp2 qx, qy;
-    __shared__ Fp s_val[QUAD_BLOCK / 4], s_pre[QUAD_BLOCK / 4];
-    auto inv = [&](const Fp& x) { return block_batch_inv(x, l4 == 0 ? slot : -1, slot, QUAD_BLOCK / 4, s_val, s_pre); };
-    bool finite = pair_to_affine(X_, inv, P, Q, px, py, qx, qy);
-    if (active && l4 == 0) flags[i] = finite ? 1 : 0;
-    DevQuadLineSink sink{lines, n, i, l4 & 1, l4 >> 1, active};
-    ate_lines_quad(X_.q, px, py, qx, qy, sink);
-}
-
-// K4a, lane-pair form of the same component-split arithmetic (quad.cuh with SIDES = 1): lanes (2j, 2j+1) hold component
-// 0 / 1 of every value of pairing j and compute the two operations of a round one after the other -- no redundant work,
-// half the warps of the four-lane form.  A pair's exchange area: 2 x 64 B + 16 B of padding.
-#define PAIR_XCH_WORDS 36
-struct DevPair {
-    static constexpr int SIDES = 1;
-    int hh;
-    uint32_t kq, xch;
-    __device__ __forceinline__ int h() const { return hh; }
-    __device__ __forceinline__ int s() const { return 0; }
-    __device__ __forceinline__ void small_reduce9(uint32_t* v, uint32_t* out) const { fp_small_reduce9(v, out, KqRowLds{kq}); }
-    __device__ __forceinline__ void partner2(const Fp& a, const Fp& b, Fp& ao, Fp& bo) const {
-        const uint32_t me = xch + (uint32_t)hh * 64, other = xch + (uint32_t)(hh ^ 1) * 64;
-        __syncwarp();  // the partner has read the previous exchange
-        DevQuad::put(me, a);
-        DevQuad::put(me + 32, b);
-        __syncwarp();
-        ao = DevQuad::get(other);
-        bo = DevQuad::get(other + 32);
-    }
-    __device__ __forceinline__ Fp partner(const Fp& a) const {
-        __syncwarp();
-        DevQuad::put(xch + (uint32_t)hh * 64, a);
-        __syncwarp();
-        return DevQuad::get(xch + (uint32_t)(hh ^ 1) * 64);
-    }
-};
-struct DevPairLineSink {
+struct DevDuoLineSink {
     uint32_t* base;
     size_t n, pidx;
     int h;
@@ -936,8 +785,11 @@ struct DevPairLineSink {
         st_fp(p + BN_LINE_OFF_XL4, L.xl4);
     }
 };
-__global__ void __launch_bounds__(DUO_BLOCK) k_pair_lines_pair(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
-                                                        uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
+#ifndef DUO_BLOCK
+#define DUO_BLOCK 32   // threads per block (run 23: 32 -> 1.589 ms, 64 -> 1.613 ms, 128 -> 1.614 ms); DUO_BLOCK/2 pairings share one batched inversion
+#endif
+__global__ void __launch_bounds__(DUO_BLOCK) k_pair_lines_duo(const uint32_t* __restrict__ g1, const uint32_t* __restrict__ g2,
+                                                       uint32_t* __restrict__ lines, uint8_t* __restrict__ flags, size_t n) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t i = t >> 1;
     const bool active = i < n;
@@ -950,21 +802,21 @@ __global__ void __launch_bounds__(DUO_BLOCK) k_pair_lines_pair(const uint32_t* _
     Q.x = ld_fp2(g2 + i * 48);
     Q.y = ld_fp2(g2 + i * 48 + 16);
     Q.z = ld_fp2(g2 + i * 48 + 32);
-    __shared__ alignas(16) uint32_t s_kq[16 * BN_KQ_STRIDE];
-    __shared__ alignas(16) uint32_t s_xch[(DUO_BLOCK / 2) * PAIR_XCH_WORDS];
+    __shared__ alignas(16) uint32_t s_kq[16 * BN_KQ_STRIDE];  // k*q rows for the xi-multiplication's reduction
+    __shared__ alignas(16) uint32_t s_xch[(DUO_BLOCK / 2) * DUO_XCH_WORDS];
     if (threadIdx.x < 16) kq_table_fill(s_kq, threadIdx.x);
     __syncthreads();
-    const int slot = (int)(threadIdx.x >> 1);
+    const int slot = (int)(threadIdx.x >> 1);  // one slot per pairing of the block
     const int h = (int)(threadIdx.x & 1);
-    QuadX<DevPair> X_{DevPair{h, smem_u32(s_kq), smem_u32(s_xch + slot * PAIR_XCH_WORDS)}};
+    DuoX<DevDuo> X_{DevDuo{h, smem_u32(s_kq), smem_u32(s_xch + slot * DUO_XCH_WORDS)}};
     Fp px, py;
     Fp2 qx, qy;
     __shared__ Fp s_val[DUO_BLOCK / 2], s_pre[DUO_BLOCK / 2];
     auto inv = [&](const Fp& x) { return block_batch_inv(x, h == 0 ? slot : -1, slot, DUO_BLOCK / 2, s_val, s_pre); };
     bool finite = pair_to_affine(X_, inv, P, Q, px, py, qx, qy);
     if (active && h == 0) flags[i] = finite ? 1 : 0;
-    DevPairLineSink sink{lines, n, i, h, active};
-    ate_lines_quad(X_.q, px, py, qx, qy, sink);
+    DevDuoLineSink sink{lines, n, i, h, active};
+    ate_lines_duo(X_.d, px, py, qx, qy, sink);
 }
 
 #ifndef HEX_MIN_BLOCKS

@@ -83,17 +83,8 @@ def lines(g1, g2, variant="product"):
 def lines_duo(g1, g2, variant="product"):
     g1, g2 = _c(g1), _c(g2)
     L = lib(variant)
-    o0 = np.zeros((L.emu_num_lines(), 40), dtype=np.uint64)
-    o1 = np.zeros((L.emu_num_lines(), 40), dtype=np.uint64)
-    finite = L.emu_lines_duo(_p(g1), _p(g2), _p(o0), _p(o1))
-    return finite, o0, o1
-
-
-def lines_quad(g1, g2, variant="product", lanes=4):
-    g1, g2 = _c(g1), _c(g2)
-    L = lib(variant)
     out = np.zeros((L.emu_num_lines(), 40), dtype=np.uint64)
-    finite = (L.emu_lines_quad if lanes == 4 else L.emu_lines_pair)(_p(g1), _p(g2), _p(out))
+    finite = L.emu_lines_duo(_p(g1), _p(g2), _p(out))
     return finite, out
 
 

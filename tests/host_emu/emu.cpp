@@ -78,10 +78,10 @@ struct HostCtx {
 };
 
 struct HostDuoShared {
-    Fp slot[2];
+    Fp pre[2][2];
     Barrier bar{2};
 };
-struct HostDuo {
+struct HostDuo {  // duo.cuh's lane-pair context: lane h owns component h
     int hh;
     HostDuoShared* sh;
     int h() const { return hh; }
@@ -91,61 +91,6 @@ struct HostDuo {
         (void)init;
         fp_small_reduce9(v, out, KqRowPtr{tab});
     }
-    Fp swap(const Fp& v) const {
-        sh->slot[hh] = v;
-        sh->bar.wait();
-        Fp r = sh->slot[hh ^ 1];
-        sh->bar.wait();
-        return r;
-    }
-};
-
-struct HostQuadShared {
-    Fp pre[4][2], post[4];
-    Barrier bar{4};
-};
-struct HostQuad {
-    static constexpr int SIDES = 2;
-    int hh, ss;
-    HostQuadShared* sh;
-    int h() const { return hh; }
-    int s() const { return ss; }
-    int me() const { return 2 * ss + hh; }
-    void small_reduce9(uint32_t* v, uint32_t* out) const { HostDuo{hh, nullptr}.small_reduce9(v, out); }
-    void partner2(const Fp& a, const Fp& b, Fp& ao, Fp& bo) const {
-        sh->pre[me()][0] = a;
-        sh->pre[me()][1] = b;
-        sh->bar.wait();
-        ao = sh->pre[me() ^ 1][0];
-        bo = sh->pre[me() ^ 1][1];
-        sh->bar.wait();
-    }
-    Fp partner(const Fp& a) const {
-        Fp ao, bo;
-        partner2(a, a, ao, bo);
-        return ao;
-    }
-    void sides(const Fp& mine, Fp& rA, Fp& rB) const {
-        sh->post[me()] = mine;
-        sh->bar.wait();
-        Fp a = sh->post[hh], b = sh->post[2 + hh];
-        sh->bar.wait();
-        rA = a;
-        rB = b;
-    }
-};
-
-struct HostPairShared {
-    Fp pre[2][2];
-    Barrier bar{2};
-};
-struct HostPair {  // quad.cuh on a lane pair (SIDES = 1)
-    static constexpr int SIDES = 1;
-    int hh;
-    HostPairShared* sh;
-    int h() const { return hh; }
-    int s() const { return 0; }
-    void small_reduce9(uint32_t* v, uint32_t* out) const { HostDuo{hh, nullptr}.small_reduce9(v, out); }
     void partner2(const Fp& a, const Fp& b, Fp& ao, Fp& bo) const {
         sh->pre[hh][0] = a;
         sh->pre[hh][1] = b;
@@ -302,52 +247,9 @@ int emu_lines(const uint64_t* g1, const uint64_t* g2, uint64_t* lines, uint64_t*
     ate_lines(X_, px, py, qx, qy, sink);
     return ok ? 1 : 0;
 }
-// same, computed by a lane PAIR (duo.cuh): two host threads; each writes its own copy, both must agree
-int emu_lines_duo(const uint64_t* g1, const uint64_t* g2, uint64_t* lines_lane0, uint64_t* lines_lane1) {
-    HostDuoShared sh;
-    int ok[2] = {0, 0};
-    uint64_t* outs[2] = {lines_lane0, lines_lane1};
-    std::vector<std::thread> th;
-    for (int h = 0; h < 2; h++)
-        th.emplace_back([&, h]() {
-            DuoX<HostDuo> X_{HostDuo{h, &sh}};
-            Fp px, py; Fp2 qx, qy;
-            ok[h] = pair_to_affine(X_, FermatInv(), load_g1(g1), load_g2(g2), px, py, qx, qy) ? 1 : 0;
-            HostLineSink sink{outs[h]};
-            ate_lines(X_, px, py, qx, qy, sink);
-        });
-    for (auto& t : th) t.join();
-    return ok[0] & ok[1];
-}
-// same, computed by FOUR lanes (quad.cuh): four host threads; each lane stores the pieces the device lane stores
-// (component h of l0 on side 0, of l3 / xl3 on side 0, of l4 / xl4 on side 1)
-struct HostQuadLineSink {
-    uint64_t* out;
-    int h, s;
-    void operator()(int t, const LineH& L) {
-        uint64_t* p = out + (size_t)t * 40;
-        if (s == 0) store_fp(p + 4 * h, L.l0);
-        store_fp(p + (s ? 24 : 8) + 4 * h, L.l3);
-        store_fp(p + (s ? 32 : 16) + 4 * h, L.xl3);
-    }
-};
-int emu_lines_quad(const uint64_t* g1, const uint64_t* g2, uint64_t* lines) {
-    HostQuadShared sh;
-    int ok[4] = {0, 0, 0, 0};
-    std::vector<std::thread> th;
-    for (int k = 0; k < 4; k++)
-        th.emplace_back([&, k]() {
-            QuadX<HostQuad> X_{HostQuad{k & 1, k >> 1, &sh}};
-            Fp px, py; Fp2 qx, qy;
-            ok[k] = pair_to_affine(X_, FermatInv(), load_g1(g1), load_g2(g2), px, py, qx, qy) ? 1 : 0;
-            HostQuadLineSink sink{lines, k & 1, k >> 1};
-            ate_lines_quad(X_.q, px, py, qx, qy, sink);
-        });
-    for (auto& t : th) t.join();
-    return ok[0] & ok[1] & ok[2] & ok[3];
-}
-// quad.cuh on a lane PAIR (SIDES = 1): lane h stores component h of every coefficient
-struct HostPairLineSink {
+// same, computed by a lane PAIR (duo.cuh): two host threads; lane h stores component h of every coefficient, as the
+// device lanes do
+struct HostDuoLineSink {
     uint64_t* out;
     int h;
     void operator()(int t, const LineH& L) {
@@ -359,17 +261,17 @@ struct HostPairLineSink {
         store_fp(p + 32, L.xl4);
     }
 };
-int emu_lines_pair(const uint64_t* g1, const uint64_t* g2, uint64_t* lines) {
-    HostPairShared sh;
+int emu_lines_duo(const uint64_t* g1, const uint64_t* g2, uint64_t* lines) {
+    HostDuoShared sh;
     int ok[2] = {0, 0};
     std::vector<std::thread> th;
-    for (int k = 0; k < 2; k++)
-        th.emplace_back([&, k]() {
-            QuadX<HostPair> X_{HostPair{k, &sh}};
+    for (int h = 0; h < 2; h++)
+        th.emplace_back([&, h]() {
+            DuoX<HostDuo> X_{HostDuo{h, &sh}};
             Fp px, py; Fp2 qx, qy;
-            ok[k] = pair_to_affine(X_, FermatInv(), load_g1(g1), load_g2(g2), px, py, qx, qy) ? 1 : 0;
-            HostPairLineSink sink{lines, k};
-            ate_lines_quad(X_.q, px, py, qx, qy, sink);
+            ok[h] = pair_to_affine(X_, FermatInv(), load_g1(g1), load_g2(g2), px, py, qx, qy) ? 1 : 0;
+            HostDuoLineSink sink{lines, h};
+            ate_lines_duo(X_.d, px, py, qx, qy, sink);
         });
     for (auto& t : th) t.join();
     return ok[0] & ok[1];

@@ -116,31 +116,18 @@ def test_naf_schedule_same_gt(pairs):
     assert np.array_equal(emu.gt_op(6, unreduced), gt[0])
 
 
-def test_duo_line_schedule_equals_solo(pairs):
-    """duo.cuh: the lane-pair line kernel produces the same 102 lines on both lanes as the one-thread version."""
-    g1, g2, _ = pairs
-    e1, e2 = util.edge_case_pairs()
-    for a, b in [(g1[0], g2[0]), (g1[1], g2[1]), (e1[0], e2[0]), (e1[6], e2[6]), (e1[1], e2[1])]:
-        finite, L, _, _ = emu.lines(a, b)
-        f2, L0, L1 = emu.lines_duo(a, b)
-        assert finite == f2
-        if finite:
-            assert np.array_equal(L, L0) and np.array_equal(L, L1)
-
-
-@pytest.mark.parametrize("lanes", [4, 2])
 @pytest.mark.parametrize("variant", ["product", "refchain"])
-def test_quad_line_schedule_equals_solo(pairs, variant, lanes):
-    """quad.cuh: the four-lane line kernel (two operations per round, one Fq2 component per lane) stores the same lines
-    as the one-thread version, for the NAF schedule and for the reference's binary chain (src/groups/mod.rs:557-588)."""
+def test_duo_line_schedule_equals_solo(pairs, variant):
+    """duo.cuh: the lane-pair line kernel (one Fq2 component per lane) stores the same lines as the one-thread version,
+    for the NAF schedule and for the reference's binary chain (102 lines, src/groups/mod.rs:557-588)."""
     g1, g2, _ = pairs
     e1, e2 = util.edge_case_pairs()
     for a, b in [(g1[0], g2[0]), (g1[1], g2[1]), (g1[2], g2[3]), (e1[0], e2[0]), (e1[6], e2[6]), (e1[1], e2[1])]:
         finite, L, _, _ = emu.lines(a, b, variant)
-        f2, Lq = emu.lines_quad(a, b, variant, lanes)
+        f2, Ld = emu.lines_duo(a, b, variant)
         assert finite == f2
         if finite:
-            assert np.array_equal(L, Lq)
+            assert np.array_equal(L, Ld)
 
 
 def test_hexad_fq12_ops(pairs):
