@@ -1,13 +1,14 @@
 #!/bin/bash
 # Run on the GPU box (via gpurun): GPU parity tests, then a short bench per line-kernel mapping.
-# usage: tools/gpu_ab3.sh <tag> "<labels>"   label = duo | solo | <variant .so name> (libv_<name>.so, default mapping)
+# usage: tools/gpu_ab3.sh <tag> "<labels>"   label = duo | solo | split<N> | <variant .so name> (libv_<name>.so, default mapping)
 TAG=$1; LABELS="$2"
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/${TAG}_pytest.txt
 cat gpurun_out/${TAG}_pytest.txt
 for v in $LABELS; do
-  unset BN_B200_SO BN_B200_LINES
+  unset BN_B200_SO BN_B200_LINES BN_B200_SPLIT
   case $v in
+    split*) export BN_B200_SPLIT=${v#split} ;;
     duo|solo) export BN_B200_LINES=$v ;;
     *) export BN_B200_SO=$PWD/bn_b200/libv_$v.so ;;
   esac
