@@ -30,7 +30,7 @@ EXPORTS = [
     "bn_b200_launch_count", "bn_b200_num_lines", "bn_b200_pairing_batch", "bn_b200_pairing_batch_dev",
     "bn_b200_pairing_batch_gather_dev", "bn_b200_pairing_kernel_name", "bn_b200_pairing_pow_batch",
     "bn_b200_pairing_pow_batch_dev", "bn_b200_scratch_bytes_per_pairing", "bn_b200_set_max_chunk",
-    "bn_b200_set_min_shard", "bn_b200_set_profiling", "bn_b200_shutdown", "bn_b200_sm_count",
+    "bn_b200_set_min_shard", "bn_b200_set_profiling", "bn_b200_set_split", "bn_b200_shutdown", "bn_b200_sm_count",
 ]
 
 

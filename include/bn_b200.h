@@ -227,6 +227,11 @@ int bn_b200_imad_peak_dev(uint32_t* d_scratch, uint32_t blocks, uint32_t iters, 
 /* Pairing batches larger than `pairs` are processed in chunks of that many pairings so that the library-owned line buffer
  * (28 160 B per pairing) stays bounded; default 2^18 (7.4 GB), 0 restores the default. */
 int bn_b200_set_max_chunk(size_t pairs);
+/* A pairing call may run as `parts` sub-batches (of at least `min_pairs` pairings each) on as many internal streams,
+ * forked from and joined to the caller's stream: results and stream ordering are unchanged, the kernels of one sub-batch
+ * fill the idle block slots of another one's last wave.  parts = 0: the library decides per call
+ * (default), 1: never, 2..4: always; min_pairs = 0: default (2048).  Same switch as the BN_B200_SPLIT environment variable. */
+int bn_b200_set_split(int parts, size_t min_pairs);
 
 /* Per-kernel device timing of the most recent pairing_batch[_dev] call, measured with CUDA events on the
  * stream the kernels were launched on (enable first; reading synchronises that stream).

@@ -358,3 +358,38 @@ def test_pairing_chunked_batches(bn):
         assert np.array_equal(bn.pairing_pow_batch(g1, g2, k), bn.gt_pow_batch(want, k))
     finally:
         lib.bn_b200_set_max_chunk(ctypes.c_size_t(0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parts", [2, 3, 4])
+def test_pairing_split_sub_batches(bn, parts):
+    """A call run as several sub-batches on the library's side streams (automatic at the headline
+    batch) gives the results of the single sequence of kernels: in place, staged host, pinned zero-copy and fused pow,
+    with ragged sub-batches (237 = 80 + 80 + 77, 120 + 117, 60 + 60 + 60 + 57) and with chunking on top."""
+    import ctypes
+    import torch
+    lib = bn.load()
+    g1, g2 = util.synth_pairs(0xB200000E, 64)
+    g1, g2 = np.tile(g1, (4, 1))[:237], np.tile(g2, (4, 1))[:237]
+    e1, e2 = util.edge_case_pairs()
+    g1[100:100 + len(e1)], g2[100:100 + len(e2)] = e1, e2
+    assert lib.bn_b200_set_split(1, ctypes.c_size_t(0)) == 0
+    try:
+        want = bn.pairing_batch(g1, g2)
+        assert np.array_equal(want[:64], cref.pairing_batch(g1[:64], g2[:64], 8))
+        assert lib.bn_b200_set_split(parts, ctypes.c_size_t(20)) == 0
+        assert np.array_equal(bn.pairing_batch(g1, g2), want)
+        h1 = torch.from_numpy(g1.view(np.int64).copy()).pin_memory()
+        h2 = torch.from_numpy(g2.view(np.int64).copy()).pin_memory()
+        ho = torch.zeros((len(g1), 48), dtype=torch.int64).pin_memory()
+        assert lib.bn_b200_pairing_batch(ctypes.c_void_p(h1.data_ptr()), ctypes.c_void_p(h2.data_ptr()),
+                                         ctypes.c_void_p(ho.data_ptr()), ctypes.c_size_t(len(g1))) == 0
+        assert np.array_equal(ho.numpy().view(np.uint64), want)
+        k = util.synth_scalars(0xB200000F, len(g1))
+        assert np.array_equal(bn.pairing_pow_batch(g1, g2, k), bn.gt_pow_batch(want, k))
+        assert lib.bn_b200_set_max_chunk(ctypes.c_size_t(150)) == 0      # 150 (split) + 87 (split)
+        assert np.array_equal(bn.pairing_batch(g1, g2), want)
+        assert lib.bn_b200_set_split(5, ctypes.c_size_t(0)) != 0
+    finally:
+        lib.bn_b200_set_max_chunk(ctypes.c_size_t(0))
+        lib.bn_b200_set_split(0, ctypes.c_size_t(0))
