@@ -6,7 +6,7 @@
 mkdir -p gpurun_out
 TAG=$1; KERNELS="$2"
 if [ "$3" = "launches" ]; then
-  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launch_bench.log 2>&1
+  BN_B200_SPLIT=1 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launch_bench.log 2>&1
 fi
 for k in $KERNELS; do
   BN_B200_SPLIT=1 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_$k python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_$k.log 2>&1
