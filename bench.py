@@ -18,6 +18,7 @@ weak scaling, plus an NCCL all-gather of the 384-byte Gt results).  Prints ONE J
 import argparse
 import ctypes
 import json
+import math
 import os
 import subprocess
 import sys
@@ -234,8 +235,10 @@ def build_roofline(m, clocks):
     if dominant in ncu_k and fresh:
         traffic = ncu_k[dominant]["dram_read_bytes"] + ncu_k[dominant]["dram_write_bytes"]
     # Pipe model (tools/ubench/pipes2.cu): scheduler cycles per warp instruction are 4.1 for
-    # IMAD.WIDE (fmaheavy), 2.19 for DFMA/DADD (FP64 pipe), 2.0 for ALU-pipe integer instructions; the pipes run
-    # concurrently, so the bound of a launch is the busiest pipe.  Instruction counts: ncu source page of THIS build.
+    # IMAD.WIDE (fmaheavy), 2.19 for DFMA/DADD (FP64 pipe), 2.0 for ALU-pipe integer instructions.  With independent
+    # instruction streams the pipes run concurrently (bound_ms = the busiest pipe); in these kernels (2-6 warps of dependent
+    # code per scheduler) the three intervals ADD UP (sum_ms), and a launch lasts as long as its busiest scheduler:
+    # model_ms = sum_ms * ceil(warps per scheduler) / (warps per scheduler).  Instruction counts: ncu source page of THIS build.
     sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
     slot = {}
     for k, v in ncu_k.items():
@@ -245,8 +248,14 @@ def build_roofline(m, clocks):
             pipes = {"fmaheavy_imad_wide": 4.1 * v["inst_imad_wide"] * scale, "fp64": 2.19 * v.get("inst_fp64", 0) * scale,
                      "alu": 2.0 * v.get("inst_alu", 0) * scale}
             bound_ms = max(pipes.values())
+            sum_ms = sum(pipes.values())
+            # warps of the launch: a lane pair per pairing (line kernel), five 6-lane hexads per warp (the others)
+            warps = math.ceil(2 * n / 32) if "lines" in k else math.ceil(n / 5)
+            wps = warps / smsp
+            model_ms = sum_ms * math.ceil(wps - 1e-9) / wps
             slot[k] = {"bound_ms": bound_ms, "busiest_pipe": max(pipes, key=pipes.get), "pipe_ms": pipes, "measured_ms": kern[k][0],
-                       "frac": bound_ms / kern[k][0], "inst_total": v["inst_total"],
+                       "frac": bound_ms / kern[k][0], "sum_ms": sum_ms, "warps_per_scheduler": wps, "model_ms": model_ms,
+                       "model_over_measured": model_ms / kern[k][0], "inst_total": v["inst_total"],
                        "issue_active_pct": v.get("smsp__issue_active.avg.pct_of_peak_sustained_active")}
     total_ms = sum(v[0] for v in kern.values())
     line_bytes = m.get("line_bytes_per_pairing", 0)
