@@ -70,6 +70,12 @@ def g2_mul(p, fr):
     return out
 
 
+def fp_mul2(a, b, c, d):
+    out = np.zeros(4, dtype=np.uint64)
+    lib().emu_fp_mul2(_p(_c(a)), _p(_c(b)), _p(_c(c)), _p(_c(d)), _p(out))
+    return out
+
+
 def lines(g1, g2, variant="product"):
     g1, g2 = _c(g1), _c(g2)
     L = lib(variant)

@@ -201,6 +201,11 @@ void emu_fp_op(int op, int which, const uint64_t* a, const uint64_t* b, uint64_t
     }
     store_fp(out, r);
 }
+// (a*b + c*d) * 2^-256 mod q with interleaved product / reduction rows (fp.cuh mul_reduce_rows); operands may be lazy
+// (<= q, or < 2q for a single product) as in duo.cuh's callers
+void emu_fp_mul2(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, uint64_t* out) {
+    store_fp(out, fp_mul2<ModQ>(load_fp(a), load_fp(b), load_fp(c), load_fp(d)));
+}
 // a * b * 2^-256 mod q through the FP64 path (f52.cuh), to be compared with emu_fp_op(0, 0, ...)
 void emu_f52_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
     const int old = std::fegetround();

@@ -46,6 +46,23 @@ def test_fp_ops(which, p):
             assert _int(emu.fp_op(7, 0, _w(a))) == pow(a * rinv % p, -1, p) * o.MONT_R % p
 
 
+def test_interleaved_multiplication_at_its_operand_bounds():
+    """fp.cuh mul_reduce_rows (product and Montgomery reduction rows on one accumulator): canonical results for the lazy
+    operands its callers pass -- q itself (the lazy negation of 0), 2q - 1 (the sums of duo.cuh's squaring) -- and for
+    a*b + c*d at its bound 2 q^2."""
+    q = o.Q
+    rinv = pow(o.MONT_R, -1, q)
+    big = [q, q - 1, 1, 0, 2**253, (q + 1) // 2] + [rnd.randrange(q) for _ in range(40)]
+    for a in big:
+        for b in (q, q - 1, rnd.choice(big)):
+            c, d = rnd.choice(big), rnd.choice(big)
+            assert _int(emu.fp_mul2(_w(a), _w(b), _w(c), _w(d))) == (a * b + c * d) * rinv % q
+    assert _int(emu.fp_mul2(_w(q), _w(q), _w(q), _w(q))) == 0
+    for x in (2 * q - 1, 2 * q - 2, q + 1, rnd.randrange(q, 2 * q)):
+        for y in (2 * q - 1, q, rnd.randrange(2 * q)):
+            assert _int(emu.fp_op(0, 0, _w(x), _w(y))) == x * y * rinv % q
+
+
 def test_fp2_ops():
     edge = [(0, 0), (o.Q - 1, o.Q - 1), (5, 0), (0, o.Q - 1), (1, 1)]
     # values straddling every multiple of q in 9x - y / 9y + x, to stress the quotient estimate
