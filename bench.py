@@ -272,7 +272,11 @@ def build_roofline(m, clocks):
                        % (M_LINES, M_MILLER, M_FEXP, M_PAIRING),
         "kernels": {k: {"ms": v[0], "achieved_timad": n / (v[0] * 1e-3) * v[1] * IMAD_PER_M / 1e12,
                         "frac": n / (v[0] * 1e-3) * v[1] * IMAD_PER_M / imad_peak} for k, v in kern.items()},
+        "kernels_note": "per-kernel times: CUDA events inside the library around ONE sequence of full-size kernels (profiling mode, as "
+                        "the ncu captures); in the timed steps a call of this size runs as two sub-batches on two streams whose kernels "
+                        "overlap (DESIGN.md section 5), so ms_per_step may be below the sum of these times",
         "whole_path_frac": (n / (total_ms * 1e-3)) * M_PAIRING * IMAD_PER_M / imad_peak,
+        "whole_path_frac_of": "the sum of the per-kernel times above (one sequence of kernels), not ms_per_step",
         "pipe_model": slot or None,
         "ncu_artefact": {"file": "profiles/ncu_kernels.json", "capture": ncu.get("source"), "matches_this_build": fresh},
         "traffic_detail": {"algorithmic_bytes_per_pairing": BYTES_IN + BYTES_OUT, "scratch_bytes_per_pairing": line_bytes,
